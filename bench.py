@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the ASW hot path (raw cost + 4 support tables + r x (V,H) + WTA).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3|cfg4|cfg5|cfg2] [--impl reference]
+
+One JSON line on stdout (rank 0).  A "step" is one pass of the hot path over this rank's
+batch of synthetic stereo pairs.  Metric: Mpix*disp/s = W*H*D*pairs / time (the reference
+thesis' own "disparities per second" metric).
+  value     : device-resident inputs, CUDA-event timed on the library's stream, max over ranks
+  e2e       : the same through asw_disparity() with pinned HOST buffers (H2D + D2H inside)
+  roofline  : dominant kernel (the slower of the V / H aggregation passes) vs the FP32 peak
+  cpu_baseline : the CPU oracle (port of the reference kernels) on a bounded sample, rank 0, N=1
+Multi-GPU: pair sharding (each rank owns its pairs, weak scaling, no data-path collective;
+one all-gather of the uint8 disparity maps at the end of a step) -- or, with --workload cfg4,
+row-band sharding of one 4K frame with a shrinking halo (strong scaling).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (synth config, pairs per rank, description)
+    "cfg2": ("cfg2_teddy_shape", 1, "synthetic 450x375, 61 disparities (Middlebury teddy/cones shape)"),
+    "cfg3": ("cfg3_1800x1500_d256", 1, "synthetic 1800x1500 pair, 256 disparities, 33-tap window, r=7"),
+    "cfg4": ("cfg4_3840x2160_d256", 1, "synthetic 3840x2160 pair, 256 disparities, row-band sharded"),
+    "cfg5": ("cfg5_1280x720_d128", 4, "synthetic 1280x720 pairs, 128 disparities, pair sharded"),
+}
+T_TAPS = 33
+FP32_PEAK_FALLBACK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # SMs x lanes x 2 x sm_max_mhz (MEASURED_PEAKS.json)
+
+
+def alg_flops(W, H, D, r):          # 8*T*r*W*H*D
+    return 8.0 * T_TAPS * r * W * H * D
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, pw, reasons = [], [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def oracle_sample(L, R, D, r, rows):
+    """Times the CPU oracle on the top `rows` rows of the workload (bounded sample)."""
+    from oracle import asw_oracle as O
+    O.lib()
+    rows = min(rows, L.shape[0])
+    Ls, Rs = np.ascontiguousarray(L[:rows]), np.ascontiguousarray(R[:rows])
+    p = O.OracleParams(ndisp=D, iterations=r)
+    t0 = time.perf_counter()
+    res = O.asw_hot_path(Ls, Rs, p, use_fma=True)
+    dt = time.perf_counter() - t0
+    W = L.shape[1]
+    return {"value": W * rows * D / dt / 1e6, "unit": "Mpix*disp/s", "cores": O.num_threads(), "kind": "port",
+            "sample": f"top {rows} of {L.shape[0]} rows of the same pair ({W}x{rows}x{D}, r={r}), {dt:.1f} s, OpenMP oracle/asw_oracle.c",
+            "seconds": dt}, res
+
+
+def run_reference_arm(args, rank):
+    """--impl reference: the reference's CPU implementation of the path (OpenMP port of its kernels;
+    the OpenCL original cannot run here) on all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    from stereo_matchin_b200 import synth
+    cfg, _, desc = WORKLOADS[args.workload]
+    L, R, _, D = synth.make_config(cfg)
+    H, W, _ = L.shape
+    rows = max(33, min(H, int(args.ref_rows)))
+    times = []
+    info = None
+    for i in range(args.warmup_ref + args.steps):
+        info, _ = oracle_sample(L, R, D, args.iterations, rows)
+        if i >= args.warmup_ref:
+            times.append(info["seconds"])
+    ms = float(np.mean(times)) * 1e3
+    v = W * rows * D / (ms * 1e-3) / 1e6
+    line = {"impl": "reference", "metric": "Mpix*disp/s (ASW agg+WTA)", "value": v, "unit": "Mpix*disp/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup_ref, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {desc}", "W": W, "H": H, "ndisp": D, "iterations": args.iterations,
+                       "sample_rows": rows},
+            "cpu_baseline": {"value": v, "unit": "Mpix*disp/s", "cores": info["cores"], "kind": "port", "sample": info["sample"]},
+            "e2e": {"value": v, "unit": "Mpix*disp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--iterations", type=int, default=7)
+    ap.add_argument("--family", type=int, default=0, help="0 = tiled kernels (default), 1 = basic kernels")
+    ap.add_argument("--cpu-rows", type=int, default=400, help="rows of the pair the CPU baseline sample covers")
+    ap.add_argument("--ref-rows", type=int, default=400)
+    ap.add_argument("--warmup-ref", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from stereo_matchin_b200 import api, synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback exists)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    cfg, pairs_per_rank, desc = WORKLOADS[args.workload]
+    W, H, D, _ = synth.CONFIGS[cfg]
+    r = args.iterations
+    band_mode = args.workload == "cfg4"
+    params = api.AswParams(ndisp=D, iterations=r)
+    ctx = api.AswContext(local_rank)
+    ctx.set_kernel_family(args.family)
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
+
+    # ---- inputs: pinned host copies and device-resident copies --------------------------------
+    if band_mode:
+        pairs = [synth.make_config(cfg, 0)[:2]]                      # every rank holds the full frame
+        y0, y1 = (H * rank) // world, (H * (rank + 1)) // world
+        band, out_rows = (y0, y1), y1 - y0
+    else:
+        pairs = [synth.make_config(cfg, rank * pairs_per_rank + i)[:2] for i in range(pairs_per_rank)]
+        band, out_rows = None, H
+    host_in = [(torch.from_numpy(L).pin_memory(), torch.from_numpy(R).pin_memory()) for L, R in pairs]
+    host_d = [torch.empty((out_rows, W), dtype=torch.uint8).pin_memory() for _ in pairs]
+    host_full_d = [torch.empty((H, W), dtype=torch.uint8).pin_memory() for _ in pairs]
+    dev_in = [(a.cuda(non_blocking=False), b.cuda(non_blocking=False)) for a, b in host_in]
+    dev_d = [torch.empty((out_rows, W), dtype=torch.uint8, device="cuda") for _ in pairs]
+    gather = torch.empty((world, len(pairs), out_rows, W), dtype=torch.uint8, device="cuda") if world > 1 and not band_mode else None
+    gather_band = torch.empty((H, W), dtype=torch.uint8, device="cuda") if world > 1 and band_mode else None
+    units_per_step_rank = W * out_rows * D * len(pairs)              # pix*disp this rank produces per step
+    torch.cuda.synchronize()
+
+    def step_device():
+        for (l, rr), o in zip(dev_in, dev_d):
+            ctx.disparity_raw(l.data_ptr(), rr.data_ptr(), W, H, params, None, o.data_ptr(), None, band=band)
+        if world > 1:   # the single collective: all-gather of the uint8 disparity maps / bands
+            with torch.cuda.stream(stream):
+                if band_mode and H % world == 0:
+                    dist.all_gather_into_tensor(gather_band, dev_d[0])
+                elif not band_mode:
+                    dist.all_gather_into_tensor(gather, torch.stack(dev_d) if len(dev_d) > 1 else dev_d[0].unsqueeze(0))
+
+    def step_host():
+        for (l, rr), o, of in zip(host_in, host_d, host_full_d):
+            if band_mode:   # upload, run the band on device pointers, download the band
+                with torch.cuda.stream(stream):
+                    dl, dr = l.cuda(non_blocking=True), rr.cuda(non_blocking=True)
+                    ctx.disparity_raw(dl.data_ptr(), dr.data_ptr(), W, H, params, None, dev_d[0].data_ptr(), None, band=band)
+                    o.copy_(dev_d[0], non_blocking=True)
+                stream.synchronize()
+            else:           # the user-facing call: host buffers in, host buffers out, synchronous
+                ctx.disparity_raw(l.data_ptr(), rr.data_ptr(), W, H, params, None, of.data_ptr(), None, host=True)
+
+    def timed(fn, steps, warm):
+        for _ in range(warm):
+            fn()
+        stream.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        stream.synchronize()
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3
+        ms = e0.elapsed_time(e1)
+        if fn is step_host and not band_mode:
+            ms = wall       # host entry point is synchronous per call: the wall clock is the honest number
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.barrier()
+        return float(t.item())
+
+    # ---- timed regions ---------------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_dev = timed(step_device, args.steps, max(args.warmup, 3))
+    clocks = sampler.stop() if rank == 0 else None
+    ms_host = timed(step_host, args.steps, 1)
+
+    total_units = units_per_step_rank
+    if world > 1:
+        tu = torch.tensor([float(units_per_step_rank)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tu)
+        total_units = float(tu.item())
+    value = total_units * args.steps / (ms_dev * 1e-3) / 1e6
+    e2e_value = total_units * args.steps / (ms_host * 1e-3) / 1e6
+
+    # ---- per-stage timing of one instrumented step (outside the timed region) ----------------------
+    tm = ctx.disparity_raw(dev_in[0][0].data_ptr(), dev_in[0][1].data_ptr(), W, H, params, None, dev_d[0].data_ptr(), None,
+                           timing=True, band=band)
+    launches_per_pair = tm["kernel_launches"]
+
+    if rank == 0:
+        # roofline of the dominant kernel: F_alg of one pass = 4*T*W*rows*D, over its mean duration
+        rows_mean = out_rows
+        if band_mode:   # halo rows computed per pass, averaged over the r iterations
+            rows_mean = float(np.mean([min(H, band[1] + (r - 1 - it) * 16) - max(0, band[0] - (r - 1 - it) * 16) for it in range(r)]))
+        pass_flops = 4.0 * T_TAPS * W * rows_mean * D
+        v_ms, h_ms = tm["vagg_mean_ms"], tm["hagg_mean_ms"]
+        dom, dom_ms = ("asw_vCostAggregation (k_vagg_t)", v_ms) if v_ms >= h_ms else ("asw_hCostAggregation (k_hagg_t)", h_ms)
+        peak, peak_src = FP32_PEAK_FALLBACK_TFLOPS, "computed: 148 SMs x 128 lanes x 2 x 1.965 GHz (MEASURED_PEAKS.json has no FP32 figure)"
+        ffma = None
+        try:
+            ub = C.CDLL(os.path.join(ROOT, "stereo_matchin_b200", "libasw_ubench.so"))
+            ub.asw_ubench_ffma_tflops.restype = C.c_double
+            ffma = {"ffma_tflops": ub.asw_ubench_ffma_tflops(0), "ffma2_tflops": ub.asw_ubench_ffma_tflops(1)}
+        except Exception as e:  # measurement helper only
+            ffma = {"error": str(e)}
+        achieved = pass_flops / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
+        peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        hbm_peak = json.load(open(peaks_file)).get("hbm_gbs") if os.path.exists(peaks_file) else 6650.0
+        Dp = (D + 31) // 32 * 32
+        pass_bytes = 3.0 * 4 * W * rows_mean * Dp      # tiled kernels: read cost + read denominator + write cost
+        roofline = {"bound": "fp32", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                    "traffic": None, "peak_source": peak_src, "measured_ffma_microbench": ffma,
+                    "whole_path_frac": alg_flops(W, rows_mean, D, r) / (tm["total_ms"] * 1e-3) / 1e12 / peak,
+                    "v_pass_ms": v_ms, "h_pass_ms": h_ms,
+                    "hbm": {"algorithmic_gbs": pass_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0, "peak_gbs": hbm_peak,
+                            "bytes_per_pass": pass_bytes}}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu, _ = oracle_sample(pairs[0][0], pairs[0][1], D, r, args.cpu_rows)
+            cpu.pop("seconds", None)
+        npx_in = sum(a.numel() + b.numel() for a, b in host_in)
+        line = {
+            "metric": "Mpix*disp/s (ASW agg+WTA, device-timed)", "value": value, "unit": "Mpix*disp/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+            "scaling": "strong" if band_mode else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {desc}", "W": W, "H": H, "ndisp": D, "radius": 16, "iterations": r,
+                       "pairs_per_rank": len(pairs), "sharding": ("row bands + shrinking halo, all-gather of bands" if band_mode
+                                                                  else "pairs (independent), all-gather of disparity maps"),
+                       "l2": "inputs larger than L2: every pass streams a %.2f GB cost volume" % (4.0 * W * H * Dp / 1e9),
+                       "kernel_family": "tiled" if args.family == 0 else "basic"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "Mpix*disp/s", "h2d_bytes_per_step": int(npx_in), "d2h_bytes_per_step": int(W * out_rows * len(pairs)),
+                    "ms_per_step": ms_host / args.steps},
+            "gpu_launches": int(launches_per_pair * len(pairs) * args.steps),
+            "stage_ms": {k: tm[k] for k in ("raw_ms", "supp_ms", "vagg_mean_ms", "hagg_mean_ms", "agg_total_ms", "wta_ms", "total_ms")},
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

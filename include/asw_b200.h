@@ -1,0 +1,180 @@
+/*
+ * asw_b200.h -- C ABI of the B200-native ASW (adaptive support weight) stereo hot path.
+ *
+ * This is the drop-in boundary for ONE path of manixq/stereo_matchin: the OpenCL ASW
+ * pipeline of stereo_matching/kernels up to winner-take-all
+ *   raw SAD cost -> 4 support-weight tables -> r x (vertical, horizontal) joint-weight
+ *   aggregation -> WTA
+ * that the reference drives from stereo_matching/main.cpp:412-526.  The reference has no
+ * plugin API: its operator surface is the six `__kernel` signatures plus the host
+ * sequence in main.cpp.  Each entry point below names the reference interface it
+ * replaces (paths relative to the reference's stereo_matching/ directory).
+ *
+ * Conventions (identical to the reference so buffers are interchangeable with it):
+ *   - images: RGBA8, tightly packed rows (pitch W*4), origin top-left
+ *     (main.cpp:189 `format = {CL_RGBA, CL_UNORM_INT8}`, main.cpp:243-244); the kernels read
+ *     them through a CLAMP_TO_EDGE / nearest sampler (main.cpp:10) and ignore alpha.
+ *   - cost volumes: float32, index x + W*y + W*H*d            (kernels/asw_aggr.cl:21)
+ *   - support tables: float32, index x + W*y + W*H*tap, tap = 0..2*radius
+ *                                                              (kernels/asw_vsupport.cl:26)
+ *   - disparity images: RGBA8, grey replicated, A = 255, grey = q8(d / (ndisp-1))
+ *                                                              (kernels/asw_wta.cl:70,73)
+ * All entry points return 0 (ASW_OK) or an asw_status code; nothing throws or exits
+ * across the ABI (the reference only prints on error, main.cpp:27-30).
+ * A context is bound to one GPU and one CUDA stream and is NOT thread-safe: use one
+ * context per GPU / host thread (the reference uses one in-order queue, main.cpp:212).
+ * There is no CPU fallback: without a CUDA device asw_create fails.
+ */
+#ifndef ASW_B200_H
+#define ASW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define ASW_API __attribute__((visibility("default")))
+#else
+#define ASW_API
+#endif
+
+typedef struct asw_ctx asw_ctx;
+
+typedef enum asw_status {
+    ASW_OK = 0,
+    ASW_ERR_INVALID = 1,      /* NULL pointer / non-positive size / bad parameter */
+    ASW_ERR_CUDA = 2,         /* a CUDA runtime call failed; see asw_last_error() */
+    ASW_ERR_NOMEM = 3,        /* device or host allocation failed */
+    ASW_ERR_UNSUPPORTED = 4   /* parameter outside the implemented range */
+} asw_status;
+
+/* Algorithm parameters.  The reference hard-codes all of them as literals; the defaults
+ * written by asw_params_default() reproduce those literals exactly. */
+typedef struct asw_params {
+    int radius;       /* support radius R, taps T = 2R+1.  16  (asw_vsupport.cl:19, asw_vcost_aggregation.cl:33,36) */
+    int ndisp;        /* number of disparities D (0..D-1). 61  (asw_aggr.cl:16, asw_wta.cl:34) */
+    float gamma_c;    /* colour bandwidth.                 30.91f (asw_vsupport.cl:22) */
+    float gamma_p;    /* proximity bandwidth.              28.21f (asw_vsupport.cl:24) */
+    float trunc;      /* raw-cost truncation; +inf = none (the reference does not truncate, asw_aggr.cl:19) */
+    int iterations;   /* r, number of (V,H) aggregation rounds. 7 (main.cpp:177) */
+} asw_params;
+
+/* Per-stage device times in milliseconds (CUDA events on the context's stream); the
+ * same columns the reference writes to its per-device log from OpenCL events
+ * (main.cpp:634-660: aggr, supp_w, v_aggr_mean, h_aggr_mean, total aggregation, wta).
+ * Stages that are fused into a neighbour report 0 and fold into agg_total_ms. */
+typedef struct asw_timing {
+    float raw_ms;         /* asw_Aggr                              (main.cpp:634) */
+    float supp_ms;        /* the four support-table launches       (main.cpp:635) */
+    float vagg_mean_ms;   /* mean vertical pass                    (main.cpp:640-644) */
+    float hagg_mean_ms;   /* mean horizontal pass                  (main.cpp:650-656) */
+    float agg_total_ms;   /* first V start .. last H end           (main.cpp:658-659) */
+    float wta_ms;         /* asw_WTA                               (main.cpp:660) */
+    float total_ms;       /* raw start .. WTA end (hot path, device only) */
+    float h2d_ms;         /* host->device upload (host-buffer entry points only) */
+    float d2h_ms;         /* device->host download */
+    int kernel_launches;  /* CUDA kernels launched by the call */
+} asw_timing;
+
+ASW_API const char* asw_version(void);
+ASW_API const char* asw_strerror(int status);
+
+/* Replaces the OpenCL platform/device/context/program/queue setup, main.cpp:119-130,158-172,210-212.
+ * `device` is a CUDA ordinal. */
+ASW_API int asw_create(asw_ctx** out, int device);
+ASW_API int asw_destroy(asw_ctx* ctx);
+ASW_API const char* asw_last_error(asw_ctx* ctx);
+/* The context's cudaStream_t (as void*), so callers can order their own work after ours. */
+ASW_API void* asw_stream(asw_ctx* ctx);
+ASW_API int asw_sync(asw_ctx* ctx);
+ASW_API int asw_device_info(asw_ctx* ctx, int* sm_count, int* sm_clock_khz, size_t* total_mem, char* name, size_t name_len);
+
+ASW_API void asw_params_default(asw_params* p);
+
+/* ---- fused hot path ---------------------------------------------------------------
+ * Replaces the enqueue sequence main.cpp:463-526 (asw_Aggr, 4x support, r x (V,H), asw_WTA)
+ * plus the upload at main.cpp:243-244 and the blocking read at main.cpp:621.
+ * Host buffers in, host buffers out; synchronous on return.  Any output may be NULL.
+ *   disp_rgba : W*H*4  left disparity image exactly as asw_WTA's `output` image
+ *   disp_d    : W*H    raw winning disparity index (uint8 when ndisp <= 256)
+ *   conf      : W*H    (min2-min1)/min2, asw_WTA's confidence_reference */
+ASW_API int asw_disparity(asw_ctx* ctx, const uint8_t* left_rgba, const uint8_t* right_rgba, int W, int H,
+                          const asw_params* prm, uint8_t* disp_rgba, uint8_t* disp_d, float* conf, asw_timing* timing);
+
+/* Same with DEVICE pointers for inputs and outputs; asynchronous on the context's stream
+ * unless `timing` is non-NULL (timing needs the events to complete). */
+ASW_API int asw_disparity_device(asw_ctx* ctx, const uint8_t* d_left_rgba, const uint8_t* d_right_rgba, int W, int H,
+                                 const asw_params* prm, uint8_t* d_disp_rgba, uint8_t* d_disp_d, float* d_conf,
+                                 asw_timing* timing);
+
+/* Row-band variant for multi-GPU sharding: computes output rows [y0, y1) of the W x H
+ * frame only.  Inputs are the FULL images (device pointers); outputs hold (y1-y0) rows.
+ * Internally rows [y0 - r*R, y1 + r*R) are processed with a halo that shrinks by R per
+ * iteration, so the band is bit-identical to the same rows of asw_disparity_device. */
+ASW_API int asw_disparity_band_device(asw_ctx* ctx, const uint8_t* d_left_rgba, const uint8_t* d_right_rgba, int W, int H,
+                                      int y0, int y1, const asw_params* prm, uint8_t* d_disp_rgba, uint8_t* d_disp_d,
+                                      float* d_conf, asw_timing* timing);
+
+/* Keep the final aggregated volume of the last asw_disparity* call (device pointer, layout
+ * above, rows of the processed band) for consumers such as the right-view WTA / consistency
+ * check.  Returns NULL if the last call did not materialise it.  Enable with
+ * asw_set_keep_volume(ctx, 1) (default 0: the last H pass feeds WTA on chip and the final
+ * volume never goes to HBM). */
+ASW_API int asw_set_keep_volume(asw_ctx* ctx, int keep);
+ASW_API const float* asw_final_volume(asw_ctx* ctx);
+
+/* ---- per-operator entry points (device pointers; reference layouts) ------------------
+ * Argument order mirrors the clSetKernelArg sequences in main.cpp; OpenCL obtained W,H
+ * from get_image_dim(), here they are explicit. */
+
+/* kernels/asw_aggr.cl:3-23 `asw_Aggr(input_l, input_r, output_cost)`; args main.cpp:463-465 */
+ASW_API int asw_Aggr(asw_ctx* ctx, const uint8_t* d_input_l, const uint8_t* d_input_r, int W, int H,
+                     const asw_params* prm, float* d_output_cost);
+/* kernels/asw_vsupport.cl:3-27 `asw_vSupport(input, output_cost)`; args main.cpp:470-471 */
+ASW_API int asw_vSupport(asw_ctx* ctx, const uint8_t* d_input, int W, int H, const asw_params* prm, float* d_output);
+/* kernels/asw_hsupport.cl:3-28 `asw_hSupport(input, output_cost)`; args main.cpp:474-475 */
+ASW_API int asw_hSupport(asw_ctx* ctx, const uint8_t* d_input, int W, int H, const asw_params* prm, float* d_output);
+/* kernels/asw_vcost_aggregation.cl:11-44
+ * `asw_vCostAggregation(input_l, supp_left, supp_right, input_cost, output_denom, output_cost)`;
+ * args main.cpp:494-499.  input_l was only used for its dimensions.  output_denom may be NULL. */
+ASW_API int asw_vCostAggregation(asw_ctx* ctx, int W, int H, const asw_params* prm, const float* d_supp_left,
+                                 const float* d_supp_right, const float* d_input_cost, float* d_output_denom,
+                                 float* d_output_cost);
+/* kernels/asw_hcost_aggregation.cl:12-44
+ * `asw_hCostAggregation(input_l, supp_left, supp_right, vertical_cost, denom_v, output_cost)`;
+ * args main.cpp:503-508.  denom_v is accepted and ignored, as in the reference (:17). */
+ASW_API int asw_hCostAggregation(asw_ctx* ctx, int W, int H, const asw_params* prm, const float* d_supp_left,
+                                 const float* d_supp_right, const float* d_vertical_cost, const float* d_denom_v,
+                                 float* d_output_cost);
+/* kernels/asw_wta.cl:12-82
+ * `asw_WTA(output_cost, output, d_est_reference, d_est_target, output_target,
+ *          confidence_reference, confidence_target)`; args main.cpp:519-525.
+ * Any output may be NULL; the right/target outputs (asw_wta.cl:50-67) are computed only
+ * if one of them is requested. */
+ASW_API int asw_WTA(asw_ctx* ctx, int W, int H, const asw_params* prm, const float* d_cost, uint8_t* d_output_rgba,
+                    float* d_est_reference, float* d_est_target, uint8_t* d_output_target_rgba,
+                    float* d_confidence_reference, float* d_confidence_target);
+
+/* ---- device memory helpers (so a plain C/C++ host needs no CUDA headers) -------------
+ * Replace clCreateBuffer / clCreateImage2D(COPY_HOST_PTR) / clEnqueueReadImage /
+ * clReleaseMemObject, main.cpp:243-256,434-457,621-629,712-738. */
+ASW_API int asw_dev_alloc(asw_ctx* ctx, void** d_ptr, size_t bytes);
+ASW_API int asw_dev_free(asw_ctx* ctx, void* d_ptr);
+ASW_API int asw_memcpy_h2d(asw_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
+ASW_API int asw_memcpy_d2h(asw_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
+/* pinned host staging memory (cudaHostAlloc) for overlapped uploads */
+ASW_API int asw_host_alloc(asw_ctx* ctx, void** h_ptr, size_t bytes);
+ASW_API int asw_host_free(asw_ctx* ctx, void* h_ptr);
+
+/* Selects the kernel family of the fused path: 0 = tiled sm_100a kernels (default),
+ * 1 = the straightforward one-thread-per-output kernels of the per-operator entry points
+ * (kept as an on-device cross-check).  Both are CUDA; neither is a CPU path. */
+ASW_API int asw_set_kernel_family(asw_ctx* ctx, int family);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASW_B200_H */

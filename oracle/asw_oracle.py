@@ -1,0 +1,174 @@
+"""ctypes binding of the CPU oracle (oracle/asw_oracle.c).
+
+TEST INFRASTRUCTURE ONLY -- importable from tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs; never from stereo_matchin_b200/.
+See the header of asw_oracle.c for scope and parity status (pinned against the
+reference's committed PNGs, tests/test_oracle_golden.py).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libasw_oracle.so")
+_lib = None
+
+
+class _Params(C.Structure):
+    _fields_ = [("radius", C.c_int), ("ndisp", C.c_int), ("gamma_c", C.c_float),
+                ("gamma_p", C.c_float), ("trunc", C.c_float), ("iterations", C.c_int)]
+
+
+@dataclass
+class OracleParams:
+    """Defaults = the reference's literals (asw_vsupport.cl:19,22,24; asw_aggr.cl:16; main.cpp:177)."""
+    radius: int = 16
+    ndisp: int = 61
+    gamma_c: float = 30.91
+    gamma_p: float = 28.21
+    trunc: float = float("inf")
+    iterations: int = 7
+
+    def c(self) -> _Params:
+        return _Params(self.radius, self.ndisp, self.gamma_c, self.gamma_p, self.trunc, self.iterations)
+
+
+def build(force: bool = False) -> str:
+    src = [os.path.join(_HERE, f) for f in ("asw_oracle.c", "asw_tail_oracle.c", "Makefile")]
+    stale = (not os.path.exists(_LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in src)
+    if force or stale:
+        subprocess.run(["make", "-C", _HERE, "-B" if force else "-s"], check=True, capture_output=True)
+    return _LIB_PATH
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB_PATH)
+        f32p, u8p = C.POINTER(C.c_float), C.POINTER(C.c_uint8)
+        _lib.oracle_num_threads.restype = C.c_int
+        _lib.oracle_set_num_threads.argtypes = [C.c_int]
+        _lib.oracle_q8.restype = C.c_uint8
+        _lib.oracle_q8.argtypes = [C.c_float]
+        _lib.oracle_asw_aggr.argtypes = [u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_float, f32p]
+        _lib.oracle_asw_vsupport.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, f32p]
+        _lib.oracle_asw_hsupport.argtypes = _lib.oracle_asw_vsupport.argtypes
+        _lib.oracle_asw_vcost_aggregation.argtypes = [f32p, f32p, f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f32p, f32p]
+        _lib.oracle_asw_hcost_aggregation.argtypes = [f32p, f32p, f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f32p]
+        _lib.oracle_asw_wta.argtypes = [f32p, C.c_int, C.c_int, C.c_int, u8p, f32p, f32p, u8p, f32p, f32p]
+        _lib.oracle_consistency.argtypes = [u8p, u8p, C.c_int, C.c_int, C.c_float, f32p, f32p, u8p, u8p]
+        _lib.oracle_asw_hot_path.restype = C.c_int
+        _lib.oracle_asw_hot_path.argtypes = [u8p, u8p, C.c_int, C.c_int, C.POINTER(_Params), C.c_int,
+                                             f32p, u8p, u8p, f32p, f32p, f32p, f32p]
+    return _lib
+
+
+def _f32(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _u8(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_uint8))
+
+
+def _img(a: np.ndarray) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    assert a.ndim == 3 and a.shape[2] == 4, "RGBA8 image expected (H, W, 4)"
+    return a
+
+
+def num_threads() -> int:
+    return lib().oracle_num_threads()
+
+
+def set_num_threads(n: int) -> None:
+    lib().oracle_set_num_threads(int(n))
+
+
+def q8(f: float) -> int:
+    return int(lib().oracle_q8(float(f)))
+
+
+def asw_aggr(left: np.ndarray, right: np.ndarray, ndisp: int = 61, trunc: float = float("inf")) -> np.ndarray:
+    left, right = _img(left), _img(right)
+    H, W, _ = left.shape
+    out = np.empty((ndisp, H, W), np.float32)
+    lib().oracle_asw_aggr(_u8(left), _u8(right), W, H, ndisp, trunc, _f32(out))
+    return out
+
+
+def asw_support(img: np.ndarray, vertical: bool, radius: int = 16, gamma_c: float = 30.91, gamma_p: float = 28.21) -> np.ndarray:
+    img = _img(img)
+    H, W, _ = img.shape
+    out = np.empty((2 * radius + 1, H, W), np.float32)
+    fn = lib().oracle_asw_vsupport if vertical else lib().oracle_asw_hsupport
+    fn(_u8(img), W, H, radius, gamma_c, gamma_p, _f32(out))
+    return out
+
+
+def asw_vcost_aggregation(supp_l, supp_r, cost, use_fma: bool = True):
+    D, H, W = cost.shape
+    R = (supp_l.shape[0] - 1) // 2
+    cost = np.ascontiguousarray(cost, np.float32)
+    out, den = np.empty_like(cost), np.empty_like(cost)
+    lib().oracle_asw_vcost_aggregation(_f32(supp_l), _f32(supp_r), _f32(cost), W, H, D, R, int(use_fma), _f32(den), _f32(out))
+    return out, den
+
+
+def asw_hcost_aggregation(supp_l, supp_r, cost, use_fma: bool = True):
+    D, H, W = cost.shape
+    R = (supp_l.shape[0] - 1) // 2
+    cost = np.ascontiguousarray(cost, np.float32)
+    out = np.empty_like(cost)
+    lib().oracle_asw_hcost_aggregation(_f32(supp_l), _f32(supp_r), _f32(cost), W, H, D, R, int(use_fma), _f32(out))
+    return out
+
+
+def asw_wta(cost: np.ndarray, right_view: bool = True) -> dict:
+    cost = np.ascontiguousarray(cost, np.float32)
+    D, H, W = cost.shape
+    r = {"left": np.empty((H, W, 4), np.uint8), "d_ref": np.empty((H, W), np.float32),
+         "conf_ref": np.empty((H, W), np.float32)}
+    if right_view:
+        r.update(right=np.empty((H, W, 4), np.uint8), d_tar=np.empty((H, W), np.float32),
+                 conf_tar=np.empty((H, W), np.float32))
+    lib().oracle_asw_wta(_f32(cost), W, H, D, _u8(r["left"]), _f32(r["d_ref"]), _f32(r.get("d_tar")),
+                         _u8(r.get("right")), _f32(r["conf_ref"]), _f32(r.get("conf_tar")))
+    return r
+
+
+def consistency(ref_rgba, tar_rgba, conf_ref=None, conf_tar=None, dscale: float = 60.0):
+    ref_rgba, tar_rgba = _img(ref_rgba), _img(tar_rgba)
+    H, W, _ = ref_rgba.shape
+    out, red = np.empty_like(ref_rgba), np.empty_like(ref_rgba)
+    lib().oracle_consistency(_u8(ref_rgba), _u8(tar_rgba), W, H, dscale, _f32(conf_ref), _f32(conf_tar), _u8(out), _u8(red))
+    return out, red
+
+
+def asw_hot_path(left: np.ndarray, right: np.ndarray, params: OracleParams | None = None, use_fma: bool = True,
+                 want_cost: bool = False, right_view: bool = False) -> dict:
+    """raw cost -> 4 support tables -> r x (V, H) -> WTA  (main.cpp:463-526)."""
+    params = params or OracleParams()
+    left, right = _img(left), _img(right)
+    H, W, _ = left.shape
+    D = params.ndisp
+    r = {"left": np.empty((H, W, 4), np.uint8), "d_ref": np.empty((H, W), np.float32),
+         "conf_ref": np.empty((H, W), np.float32)}
+    if want_cost:
+        r["cost"] = np.empty((D, H, W), np.float32)
+    if right_view:
+        r.update(right=np.empty((H, W, 4), np.uint8), d_tar=np.empty((H, W), np.float32),
+                 conf_tar=np.empty((H, W), np.float32))
+    p = params.c()
+    rc = lib().oracle_asw_hot_path(_u8(left), _u8(right), W, H, C.byref(p), int(use_fma), _f32(r.get("cost")),
+                                   _u8(r["left"]), _u8(r.get("right")), _f32(r["d_ref"]), _f32(r.get("d_tar")),
+                                   _f32(r["conf_ref"]), _f32(r.get("conf_tar")))
+    if rc != 0:
+        raise RuntimeError(f"oracle_asw_hot_path failed rc={rc}")
+    return r

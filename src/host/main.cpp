@@ -1,0 +1,134 @@
+// main.cpp -- the pics.txt-driven host flow of the reference's stereo_matching/main.cpp, for the
+// ASW hot path only, on top of the C ABI (include/asw_b200.h).  What is kept from the reference:
+//   * pics.txt: pairs of whitespace-separated tokens, left then right (main.cpp:134-148);
+//     the output folder is the path prefix before the first '/' (main.cpp:151-156)
+//   * per image: decode both PNGs to RGBA8 (main.cpp:183-186), 10 runs (main.cpp:213),
+//     PNG written from the first run, per-run timing row in a TSV log named after the device
+//     (main.cpp:164-166,179-181,634-708) with the reference's column names
+//   * per-stage timings come from device events (CL profiling there, CUDA events here)
+// What is replaced: the OpenCL platform/device/context/program/queue setup and the enqueue
+// sequence (main.cpp:119-130,158-172,210-256,434-526) -> asw_create + asw_disparity.
+// Out of scope (columns written as 0): the cross-based method and the refinement tail.
+//
+// Usage: stereo_matching [--pics pics.txt] [--root DIR] [--runs 10] [--device 0] [--ndisp 61]
+//                        [--iterations 7] [--out-suffix _wta] [--log FILE]
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <string>
+#include <vector>
+
+#include "asw_b200.h"
+#include "png_io.h"
+
+struct Image {
+    std::vector<unsigned char> pixel;
+    unsigned width = 0, height = 0;
+};
+
+static const char* kHeader =
+    "id\tmedL_solo\tmedR_solo\tmed_full\tcross_h\tcross_v\tcross_full\taggregation\tintegral_h\taggr_h\tintegral_v\taggr_v\t"
+    "init_disp\tfinal_disp\tcross method total\t\t\taggr\tsupp_w\tv_aggr_mean\th_aggr_mean\ttotal aggregation\twta\t"
+    "consistency\tv_ref_mean_L\tv_ref_mean_R\th_ref_mean_L\th_ref_mean_R\twta_mean_LR\tconsistency_mean\ttotal refinement\t"
+    "median\ttotal WTA method";   // main.cpp:181
+
+int main(int argc, char** argv) {
+    std::string pics = "pics.txt", root = ".", suffix = "_wta", log_name;
+    int runs = 10, device = 0;
+    asw_params prm;
+    asw_params_default(&prm);
+    for (int i = 1; i < argc; i++) {
+        std::string a = argv[i];
+        auto next = [&](const char* what) -> const char* {
+            if (i + 1 >= argc) { fprintf(stderr, "missing value for %s\n", what); exit(2); }
+            return argv[++i];
+        };
+        if (a == "--pics") pics = next("--pics");
+        else if (a == "--root") root = next("--root");
+        else if (a == "--runs") runs = atoi(next("--runs"));
+        else if (a == "--device") device = atoi(next("--device"));
+        else if (a == "--ndisp") prm.ndisp = atoi(next("--ndisp"));
+        else if (a == "--iterations") prm.iterations = atoi(next("--iterations"));
+        else if (a == "--out-suffix") suffix = next("--out-suffix");
+        else if (a == "--log") log_name = next("--log");
+        else { fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
+    }
+
+    // read image paths: pairs of tokens (main.cpp:134-148)
+    std::vector<std::string> left_path, right_path, folder_name;
+    {
+        std::ifstream in(pics);
+        if (!in) { fprintf(stderr, "cannot open %s\n", pics.c_str()); return 1; }
+        std::string l, r;
+        while (in >> l >> r) {
+            left_path.push_back(l);
+            right_path.push_back(r);
+            folder_name.push_back(l.substr(0, l.find('/')));   // main.cpp:151-156
+        }
+    }
+
+    asw_ctx* ctx = nullptr;
+    int st = asw_create(&ctx, device);
+    if (st != ASW_OK) {
+        fprintf(stderr, "asw_create(device %d) failed: %s (a CUDA device is required)\n", device, asw_strerror(st));
+        return 1;
+    }
+    char dev_name[256] = "";
+    asw_device_info(ctx, nullptr, nullptr, nullptr, dev_name, sizeof dev_name);
+    printf("\t- Device name: %s\n", dev_name);
+    if (log_name.empty()) log_name = root + "/" + dev_name;     // log named after the device (main.cpp:164-166)
+    FILE* to_file = fopen(log_name.c_str(), "w");
+    if (!to_file) { fprintf(stderr, "cannot open log %s\n", log_name.c_str()); asw_destroy(ctx); return 1; }
+
+    int rc = 0;
+    for (size_t img = 0; img < left_path.size(); img++) {
+        fprintf(to_file, "\n%s - %s\n", dev_name, folder_name[img].c_str());
+        printf("\n%s\n", folder_name[img].c_str());
+        fprintf(to_file, "%s", kHeader);
+        Image imgL, imgR;
+        unsigned e1 = png_io::decode(imgL.pixel, imgL.width, imgL.height, root + "/" + left_path[img]);
+        unsigned e2 = png_io::decode(imgR.pixel, imgR.width, imgR.height, root + "/" + right_path[img]);
+        if (e1 || e2 || imgL.width != imgR.width || imgL.height != imgR.height) {
+            fprintf(stderr, "cannot load pair %s / %s: %s\n", left_path[img].c_str(), right_path[img].c_str(),
+                    png_io::error_text(e1 ? e1 : e2));
+            rc = 1;
+            continue;
+        }
+        const unsigned W = imgL.width, H = imgL.height;
+        std::vector<unsigned char> disp((size_t)W * H * 4);
+        double sum_total = 0;
+        for (int run = 0; run < runs; run++) {
+            fprintf(to_file, "\nRun %d \t", run + 1);
+            printf("\n---Working...\nRaw cost aggregation..  \ngestalt principle - support area.. \nCost aggregation.. \nWTA.. ");
+            asw_timing t;
+            st = asw_disparity(ctx, imgL.pixel.data(), imgR.pixel.data(), (int)W, (int)H, &prm, disp.data(), nullptr, nullptr, &t);
+            if (st != ASW_OK) {
+                printf("ASW error executing hot path: %d (%s)\n", st, asw_last_error(ctx));   // ErCheck prints and continues
+                rc = 1;
+                continue;
+            }
+            if (run == 0) {   // the reference's PNGs on disk come from run 1
+                std::string out = root + "/" + folder_name[img] + "/asw_disparity" + suffix + ".png";
+                unsigned e = png_io::encode(out, disp, W, H);
+                if (e) { fprintf(stderr, "cannot write %s: %s\n", out.c_str(), png_io::error_text(e)); rc = 1; }
+            }
+            for (int c = 0; c < 14; c++) fprintf(to_file, "%0.3f\t", 0.0);   // cross-based columns: out of scope
+            fprintf(to_file, "\t\t");
+            fprintf(to_file, "%0.3f\t%0.3f\t%0.3f\t%0.3f\t%0.3f\t%0.3f\t", t.raw_ms, t.supp_ms, t.vagg_mean_ms, t.hagg_mean_ms,
+                    t.agg_total_ms, t.wta_ms);
+            for (int c = 0; c < 9; c++) fprintf(to_file, "%0.3f\t", 0.0);    // consistency / refinement / median: next rows
+            fprintf(to_file, "%0.3f\t", t.total_ms);
+            sum_total += t.total_ms;
+        }
+        if (runs > 0) {
+            double ms = sum_total / runs;
+            printf("\n%s: %ux%u, %d disparities, r = %d: %.3f ms/frame (device), %.1f Mpix*disp/s\n", folder_name[img].c_str(), W, H,
+                   prm.ndisp, prm.iterations, ms, ms > 0 ? (double)W * H * prm.ndisp / ms / 1e3 : 0.0);
+        }
+    }
+    fclose(to_file);
+    asw_destroy(ctx);
+    return rc;
+}

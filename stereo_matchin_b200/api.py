@@ -1,0 +1,298 @@
+"""ctypes binding of the C ABI (include/asw_b200.h) -- the host-side mirror of the reference's
+operator surface for the ASW hot path (kernels/asw_*.cl + the enqueue sequence of
+stereo_matching/main.cpp:463-526).
+
+The product is libasw_b200.so (hand-written CUDA for sm_100a).  This module only marshals
+arguments: numpy arrays for host buffers, integer device addresses (e.g. torch
+``tensor.data_ptr()``) for device buffers.  There is no CPU fallback: if the library is
+missing or no CUDA device is present, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libasw_b200.so")
+
+ASW_OK, ASW_ERR_INVALID, ASW_ERR_CUDA, ASW_ERR_NOMEM, ASW_ERR_UNSUPPORTED = range(5)
+
+# every symbol include/asw_b200.h declares (tests check the library exports all of them)
+EXPORTS = [
+    "asw_version", "asw_strerror", "asw_create", "asw_destroy", "asw_last_error", "asw_stream", "asw_sync",
+    "asw_device_info", "asw_params_default", "asw_disparity", "asw_disparity_device", "asw_disparity_band_device",
+    "asw_set_keep_volume", "asw_final_volume", "asw_Aggr", "asw_vSupport", "asw_hSupport", "asw_vCostAggregation",
+    "asw_hCostAggregation", "asw_WTA", "asw_dev_alloc", "asw_dev_free", "asw_memcpy_h2d", "asw_memcpy_d2h",
+    "asw_host_alloc", "asw_host_free", "asw_set_kernel_family",
+]
+
+
+class AswError(RuntimeError):
+    def __init__(self, status: int, msg: str):
+        super().__init__(f"asw_b200 status {status}: {msg}")
+        self.status = status
+
+
+class CParams(C.Structure):
+    _fields_ = [("radius", C.c_int), ("ndisp", C.c_int), ("gamma_c", C.c_float), ("gamma_p", C.c_float),
+                ("trunc", C.c_float), ("iterations", C.c_int)]
+
+
+class CTiming(C.Structure):
+    _fields_ = [("raw_ms", C.c_float), ("supp_ms", C.c_float), ("vagg_mean_ms", C.c_float), ("hagg_mean_ms", C.c_float),
+                ("agg_total_ms", C.c_float), ("wta_ms", C.c_float), ("total_ms", C.c_float), ("h2d_ms", C.c_float),
+                ("d2h_ms", C.c_float), ("kernel_launches", C.c_int)]
+
+    def as_dict(self) -> dict:
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+@dataclass
+class AswParams:
+    """Defaults reproduce the reference's literals (asw_vsupport.cl:19,22,24; asw_aggr.cl:16; main.cpp:177)."""
+    radius: int = 16
+    ndisp: int = 61
+    gamma_c: float = 30.91
+    gamma_p: float = 28.21
+    trunc: float = math.inf
+    iterations: int = 7
+
+    def c(self) -> CParams:
+        return CParams(self.radius, self.ndisp, self.gamma_c, self.gamma_p, self.trunc, self.iterations)
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Loads libasw_b200.so (never builds, never falls back)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FileNotFoundError(f"{LIB_PATH} is missing: run `python -m stereo_matchin_b200.build` (needs nvcc)")
+    lib = C.CDLL(LIB_PATH)
+    vp, u8p, f32p, ip = C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)
+    pp, tp = C.POINTER(CParams), C.POINTER(CTiming)
+    lib.asw_version.restype = C.c_char_p
+    lib.asw_strerror.restype = C.c_char_p
+    lib.asw_strerror.argtypes = [C.c_int]
+    lib.asw_create.argtypes = [C.POINTER(vp), C.c_int]
+    lib.asw_destroy.argtypes = [vp]
+    lib.asw_last_error.restype = C.c_char_p
+    lib.asw_last_error.argtypes = [vp]
+    lib.asw_stream.restype = vp
+    lib.asw_stream.argtypes = [vp]
+    lib.asw_sync.argtypes = [vp]
+    lib.asw_device_info.argtypes = [vp, ip, ip, C.POINTER(C.c_size_t), C.c_char_p, C.c_size_t]
+    lib.asw_params_default.argtypes = [pp]
+    lib.asw_params_default.restype = None
+    lib.asw_disparity.argtypes = [vp, u8p, u8p, C.c_int, C.c_int, pp, u8p, u8p, f32p, tp]
+    lib.asw_disparity_device.argtypes = [vp, u8p, u8p, C.c_int, C.c_int, pp, u8p, u8p, f32p, tp]
+    lib.asw_disparity_band_device.argtypes = [vp, u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, pp, u8p, u8p, f32p, tp]
+    lib.asw_set_keep_volume.argtypes = [vp, C.c_int]
+    lib.asw_final_volume.restype = vp
+    lib.asw_final_volume.argtypes = [vp]
+    lib.asw_Aggr.argtypes = [vp, u8p, u8p, C.c_int, C.c_int, pp, f32p]
+    lib.asw_vSupport.argtypes = [vp, u8p, C.c_int, C.c_int, pp, f32p]
+    lib.asw_hSupport.argtypes = [vp, u8p, C.c_int, C.c_int, pp, f32p]
+    lib.asw_vCostAggregation.argtypes = [vp, C.c_int, C.c_int, pp, f32p, f32p, f32p, f32p, f32p]
+    lib.asw_hCostAggregation.argtypes = [vp, C.c_int, C.c_int, pp, f32p, f32p, f32p, f32p, f32p]
+    lib.asw_WTA.argtypes = [vp, C.c_int, C.c_int, pp, f32p, u8p, f32p, f32p, u8p, f32p, f32p]
+    lib.asw_dev_alloc.argtypes = [vp, C.POINTER(vp), C.c_size_t]
+    lib.asw_dev_free.argtypes = [vp, vp]
+    lib.asw_memcpy_h2d.argtypes = [vp, vp, vp, C.c_size_t]
+    lib.asw_memcpy_d2h.argtypes = [vp, vp, vp, C.c_size_t]
+    lib.asw_host_alloc.argtypes = [vp, C.POINTER(vp), C.c_size_t]
+    lib.asw_host_free.argtypes = [vp, vp]
+    lib.asw_set_kernel_family.argtypes = [vp, C.c_int]
+    _lib = lib
+    return lib
+
+
+def default_params() -> AswParams:
+    p = CParams()
+    load_library().asw_params_default(C.byref(p))
+    return AswParams(p.radius, p.ndisp, p.gamma_c, p.gamma_p, p.trunc, p.iterations)
+
+
+def _host_ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+def _rgba(a: np.ndarray) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    if a.ndim != 3 or a.shape[2] != 4:
+        raise ValueError("RGBA8 image of shape (H, W, 4) expected")
+    return a
+
+
+class DeviceBuffer:
+    """A device allocation owned through the ABI (asw_dev_alloc / asw_dev_free)."""
+
+    def __init__(self, ctx: "AswContext", nbytes: int):
+        self.ctx, self.nbytes = ctx, int(nbytes)
+        p = C.c_void_p()
+        ctx._check(ctx.lib.asw_dev_alloc(ctx.h, C.byref(p), self.nbytes))
+        self.ptr = p.value
+
+    def upload(self, a: np.ndarray) -> "DeviceBuffer":
+        a = np.ascontiguousarray(a)
+        assert a.nbytes <= self.nbytes
+        self.ctx._check(self.ctx.lib.asw_memcpy_h2d(self.ctx.h, self.ptr, a.ctypes.data, a.nbytes))
+        return self
+
+    def download(self, shape, dtype) -> np.ndarray:
+        out = np.empty(shape, dtype)
+        assert out.nbytes <= self.nbytes
+        self.ctx._check(self.ctx.lib.asw_memcpy_d2h(self.ctx.h, out.ctypes.data, self.ptr, out.nbytes))
+        return out
+
+    def free(self):
+        if self.ptr:
+            self.ctx.lib.asw_dev_free(self.ctx.h, self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class AswContext:
+    """One GPU + one stream (the reference's context + in-order queue, main.cpp:170-171,212)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        st = self.lib.asw_create(C.byref(h), int(device))
+        if st != ASW_OK:
+            raise AswError(st, f"asw_create(device={device}) failed: {self.lib.asw_strerror(st).decode()} "
+                               "(a CUDA device is required; there is no CPU fallback)")
+        self.h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.asw_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st: int):
+        if st != ASW_OK:
+            raise AswError(st, f"{self.lib.asw_strerror(st).decode()}: {self.lib.asw_last_error(self.h).decode()}")
+
+    # -- misc ------------------------------------------------------------------------------------
+    def stream(self) -> int:
+        return int(self.lib.asw_stream(self.h) or 0)
+
+    def sync(self):
+        self._check(self.lib.asw_sync(self.h))
+
+    def device_info(self) -> dict:
+        sm, khz, mem = C.c_int(), C.c_int(), C.c_size_t()
+        name = C.create_string_buffer(256)
+        self._check(self.lib.asw_device_info(self.h, C.byref(sm), C.byref(khz), C.byref(mem), name, 256))
+        return {"sm_count": sm.value, "sm_clock_khz": khz.value, "total_mem": mem.value, "name": name.value.decode()}
+
+    def set_kernel_family(self, family: int):
+        self._check(self.lib.asw_set_kernel_family(self.h, family))
+
+    def set_keep_volume(self, keep: bool):
+        self._check(self.lib.asw_set_keep_volume(self.h, int(keep)))
+
+    def alloc(self, nbytes: int) -> DeviceBuffer:
+        return DeviceBuffer(self, nbytes)
+
+    def to_device(self, a: np.ndarray) -> DeviceBuffer:
+        a = np.ascontiguousarray(a)
+        return DeviceBuffer(self, a.nbytes).upload(a)
+
+    # -- fused hot path ----------------------------------------------------------------------------
+    def disparity(self, left: np.ndarray, right: np.ndarray, params: AswParams | None = None, want_conf: bool = True,
+                  want_timing: bool = False) -> dict:
+        """Host buffers in, host buffers out (asw_disparity): the call a user of the reference makes."""
+        params = params or AswParams()
+        left, right = _rgba(left), _rgba(right)
+        if left.shape != right.shape:
+            raise ValueError("left and right images must have the same shape")
+        H, W, _ = left.shape
+        out = {"disp_rgba": np.empty((H, W, 4), np.uint8),
+               "disp_d": np.empty((H, W), np.uint8) if params.ndisp <= 256 else None,
+               "conf": np.empty((H, W), np.float32) if want_conf else None}
+        tm = CTiming() if want_timing else None
+        p = params.c()
+        self._check(self.lib.asw_disparity(self.h, left.ctypes.data, right.ctypes.data, W, H, C.byref(p),
+                                           _host_ptr(out["disp_rgba"]), _host_ptr(out["disp_d"]), _host_ptr(out["conf"]),
+                                           C.byref(tm) if tm is not None else None))
+        if tm is not None:
+            out["timing"] = tm.as_dict()
+        return out
+
+    def disparity_raw(self, left_ptr: int, right_ptr: int, W: int, H: int, params: AswParams, rgba_ptr: int | None,
+                      d_ptr: int | None, conf_ptr: int | None, timing: bool = False, host: bool = False,
+                      band: tuple[int, int] | None = None) -> dict | None:
+        """Pointer-level call: host pointers (host=True, asw_disparity) or device pointers."""
+        tm = CTiming() if timing else None
+        p = params.c()
+        tref = C.byref(tm) if tm is not None else None
+        if host:
+            st = self.lib.asw_disparity(self.h, left_ptr, right_ptr, W, H, C.byref(p), rgba_ptr, d_ptr, conf_ptr, tref)
+        elif band is not None:
+            st = self.lib.asw_disparity_band_device(self.h, left_ptr, right_ptr, W, H, band[0], band[1], C.byref(p), rgba_ptr,
+                                                    d_ptr, conf_ptr, tref)
+        else:
+            st = self.lib.asw_disparity_device(self.h, left_ptr, right_ptr, W, H, C.byref(p), rgba_ptr, d_ptr, conf_ptr, tref)
+        self._check(st)
+        return tm.as_dict() if tm is not None else None
+
+    def final_volume_ptr(self) -> int:
+        return int(self.lib.asw_final_volume(self.h) or 0)
+
+    # -- per-operator entry points (device pointers, reference layouts) ----------------------------
+    def asw_Aggr(self, input_l: int, input_r: int, W: int, H: int, params: AswParams, output_cost: int):
+        p = params.c()
+        self._check(self.lib.asw_Aggr(self.h, input_l, input_r, W, H, C.byref(p), output_cost))
+
+    def asw_vSupport(self, input_: int, W: int, H: int, params: AswParams, output: int):
+        p = params.c()
+        self._check(self.lib.asw_vSupport(self.h, input_, W, H, C.byref(p), output))
+
+    def asw_hSupport(self, input_: int, W: int, H: int, params: AswParams, output: int):
+        p = params.c()
+        self._check(self.lib.asw_hSupport(self.h, input_, W, H, C.byref(p), output))
+
+    def asw_vCostAggregation(self, W: int, H: int, params: AswParams, supp_left: int, supp_right: int, input_cost: int,
+                             output_denom: int | None, output_cost: int):
+        p = params.c()
+        self._check(self.lib.asw_vCostAggregation(self.h, W, H, C.byref(p), supp_left, supp_right, input_cost, output_denom,
+                                                  output_cost))
+
+    def asw_hCostAggregation(self, W: int, H: int, params: AswParams, supp_left: int, supp_right: int, vertical_cost: int,
+                             denom_v: int | None, output_cost: int):
+        p = params.c()
+        self._check(self.lib.asw_hCostAggregation(self.h, W, H, C.byref(p), supp_left, supp_right, vertical_cost, denom_v,
+                                                  output_cost))
+
+    def asw_WTA(self, W: int, H: int, params: AswParams, cost: int, output: int | None, d_est_reference: int | None,
+                d_est_target: int | None, output_target: int | None, confidence_reference: int | None,
+                confidence_target: int | None):
+        p = params.c()
+        self._check(self.lib.asw_WTA(self.h, W, H, C.byref(p), cost, output, d_est_reference, d_est_target, output_target,
+                                     confidence_reference, confidence_target))

@@ -1,0 +1,501 @@
+// asw_api.cu -- the extern "C" boundary (include/asw_b200.h) and the host sequence of the
+// ASW hot path.  Replaces the OpenCL runtime glue and enqueue sequence of the reference's
+// stereo_matching/main.cpp:119-130,158-172,210-256,434-526,621 with CUDA: one context =
+// one GPU + one stream + grow-on-demand device scratch (allocation stays outside the
+// timed region, as in the reference where clCreateBuffer precedes the first event).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+
+#include "../../include/asw_b200.h"
+#include "asw_common.cuh"
+#include "asw_kernels_basic.cuh"
+#include "asw_kernels_tiled.cuh"
+
+using namespace asw;
+
+namespace {
+
+struct Scratch {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct asw_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaDeviceProp prop{};
+    std::string err;
+    int family = 0;
+    int keep_volume = 0;
+    const float* final_volume = nullptr;
+    int launches = 0;
+    // device scratch, reused across calls
+    Scratch img_l, img_r;                  // uploads (host entry point)
+    Scratch out_rgba, out_d, out_conf;     // downloads (host entry point)
+    Scratch vL, hL, vR, hR;                // support tables
+    Scratch vol[3];                        // cost volumes (raw / ping / pong)
+    Scratch den_v, den_h;                  // hoisted denominators
+    Scratch vol_ref;                       // final volume in the reference layout (keep_volume)
+    enum { kMaxEvents = 64 };
+    cudaEvent_t ev[kMaxEvents] = {};
+};
+
+namespace {
+
+int fail(asw_ctx* c, int status, const char* what, cudaError_t e = cudaSuccess) {
+    if (c) {
+        char buf[512];
+        if (e != cudaSuccess) snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+        else snprintf(buf, sizeof buf, "%s", what);
+        c->err = buf;
+    }
+    return status;
+}
+
+#define CU(call)                                                        \
+    do {                                                                \
+        cudaError_t e__ = (call);                                       \
+        if (e__ != cudaSuccess) return fail(ctx, ASW_ERR_CUDA, #call, e__); \
+    } while (0)
+
+int ensure(asw_ctx* ctx, Scratch& s, size_t bytes) {
+    if (s.cap >= bytes) return ASW_OK;
+    if (s.p) { cudaFree(s.p); s.p = nullptr; s.cap = 0; }
+    cudaError_t e = cudaMalloc(&s.p, bytes);
+    if (e != cudaSuccess) { s.p = nullptr; cudaGetLastError(); return fail(ctx, ASW_ERR_NOMEM, "cudaMalloc scratch", e); }
+    s.cap = bytes;
+    return ASW_OK;
+}
+
+int check_params(asw_ctx* ctx, int W, int H, const asw_params* p) {
+    if (!ctx) return ASW_ERR_INVALID;
+    if (!p) return fail(ctx, ASW_ERR_INVALID, "params is NULL");
+    if (W <= 0 || H <= 0) return fail(ctx, ASW_ERR_INVALID, "W and H must be positive");
+    if (p->ndisp <= 0 || p->radius < 0 || p->iterations < 0) return fail(ctx, ASW_ERR_INVALID, "ndisp > 0, radius >= 0, iterations >= 0 required");
+    if (!(p->gamma_c > 0.0f) || !(p->gamma_p > 0.0f)) return fail(ctx, ASW_ERR_INVALID, "gamma_c and gamma_p must be positive");
+    if (p->ndisp > 65535 || H > 65535) return fail(ctx, ASW_ERR_UNSUPPORTED, "ndisp and H are limited to 65535");
+    if (p->radius > 64) return fail(ctx, ASW_ERR_UNSUPPORTED, "radius is limited to 64");
+    return ASW_OK;
+}
+
+inline dim3 grid3(int W, int rows, int z, int bx) { return dim3((unsigned)((W + bx - 1) / bx), (unsigned)rows, (unsigned)z); }
+
+// ---- basic-family launches (also the per-operator entry points) -----------------------
+int launch_raw(asw_ctx* ctx, const uint8_t* l, const uint8_t* r, Band b, int ylo, int yhi, const asw_params* p, float* cost) {
+    if (yhi <= ylo) return ASW_OK;
+    int gz = p->ndisp < 8 ? p->ndisp : 8;
+    k_raw_cost<<<grid3(b.W, yhi - ylo, gz, 128), 128, 0, ctx->stream>>>((const uint32_t*)l, (const uint32_t*)r, b, ylo, yhi,
+                                                                      p->ndisp, p->trunc, cost);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return ASW_OK;
+}
+
+int launch_support(asw_ctx* ctx, bool vertical, const uint8_t* img, Band b, int ylo, int yhi, const asw_params* p, float* out) {
+    if (yhi <= ylo) return ASW_OK;
+    dim3 g = grid3(b.W, yhi - ylo, 2 * p->radius + 1, 128);
+    if (vertical) k_support<true><<<g, 128, 0, ctx->stream>>>((const uint32_t*)img, b, ylo, yhi, p->radius, p->gamma_c, p->gamma_p, out);
+    else k_support<false><<<g, 128, 0, ctx->stream>>>((const uint32_t*)img, b, ylo, yhi, p->radius, p->gamma_c, p->gamma_p, out);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return ASW_OK;
+}
+
+int launch_agg_basic(asw_ctx* ctx, bool vertical, Band b, int ylo, int yhi, const asw_params* p, const float* sL,
+                     const float* sR, const float* cin, float* den, float* cout) {
+    if (yhi <= ylo) return ASW_OK;
+    dim3 g = grid3(b.W, yhi - ylo, p->ndisp, 128);
+    if (vertical) k_aggregate<true><<<g, 128, 0, ctx->stream>>>(sL, sR, cin, b, ylo, yhi, p->radius, den, cout);
+    else k_aggregate<false><<<g, 128, 0, ctx->stream>>>(sL, sR, cin, b, ylo, yhi, p->radius, den, cout);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return ASW_OK;
+}
+
+int launch_wta(asw_ctx* ctx, Band b, int ylo, int yhi, int out_y0, const asw_params* p, const float* cost, uint8_t* rgba,
+               uint8_t* dd, float* d_ref, float* d_tar, uint8_t* tar_rgba, float* conf_ref, float* conf_tar) {
+    if (yhi <= ylo) return ASW_OK;
+    k_wta<<<grid3(b.W, yhi - ylo, 1, 128), 128, 0, ctx->stream>>>(cost, b, ylo, yhi, p->ndisp, out_y0, (uint32_t*)rgba, dd, d_ref,
+                                                                 d_tar, (uint32_t*)tar_rgba, conf_ref, conf_tar);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return ASW_OK;
+}
+
+struct EvTimer {
+    asw_ctx* ctx;
+    bool on;
+    int n = 0;
+    int mark() {
+        if (!on || n >= asw_ctx::kMaxEvents) return -1;
+        cudaEventRecord(ctx->ev[n], ctx->stream);
+        return n++;
+    }
+    float ms(int a, int b) const {
+        if (!on || a < 0 || b < 0) return 0.f;
+        float t = 0.f;
+        cudaEventElapsedTime(&t, ctx->ev[a], ctx->ev[b]);
+        return t;
+    }
+};
+
+// Records the stage boundaries of one run and turns them into the reference's log columns.
+struct StageTimes {
+    EvTimer et;
+    int e_start = -1, e_raw = -1, e_supp = -1, e_agg = -1, e_wta = -1;
+    bool pass_marks = false;
+    void fill(asw_timing* tm, int r, int launches) {
+        memset(tm, 0, sizeof *tm);
+        tm->raw_ms = et.ms(e_start, e_raw);
+        tm->supp_ms = et.ms(e_raw, e_supp);
+        float vsum = 0.f, hsum = 0.f;
+        for (int it = 0; pass_marks && it < r; it++) {   // marks after e_supp alternate V, H
+            const int ev_v = e_supp + 1 + 2 * it;
+            vsum += et.ms(ev_v - 1, ev_v);
+            hsum += et.ms(ev_v, ev_v + 1);
+        }
+        tm->vagg_mean_ms = r ? vsum / r : 0.f;
+        tm->hagg_mean_ms = r ? hsum / r : 0.f;
+        tm->agg_total_ms = et.ms(e_supp, e_agg);
+        tm->wta_ms = et.ms(e_agg, e_wta);
+        tm->total_ms = et.ms(e_start, e_wta);
+        tm->kernel_launches = launches;
+    }
+};
+
+#define CUL(call)                                                                          \
+    do {                                                                                   \
+        cudaError_t e__ = (call);                                                          \
+        ctx->launches++;                                                                   \
+        if (e__ != cudaSuccess) return fail(ctx, ASW_ERR_CUDA, #call, e__);                \
+    } while (0)
+
+// The hot path on device buffers for output rows [y0, y1) of a W x H frame (main.cpp:463-526).
+int run_band(asw_ctx* ctx, const uint8_t* dl, const uint8_t* dr, int W, int H, int y0, int y1, const asw_params* p,
+             uint8_t* d_rgba, uint8_t* d_d, float* d_conf, asw_timing* tm) {
+    const int R = p->radius, T = 2 * R + 1, D = p->ndisp, r = p->iterations;
+    // rows whose values can influence rows [y0,y1): R rows per V pass (H passes stay in-row)
+    const int ya = max(0, y0 - r * R), yb = min(H, y1 + r * R);
+    Band b{W, H, ya, yb - ya};
+    const bool tiled = ctx->family == 0 && tiled_supported(R);
+    const int Dp = tiled ? padded_D(D) : D;
+    const size_t vol_bytes = sizeof(float) * b.plane() * (size_t)Dp;
+    const size_t tab_bytes = sizeof(float) * b.plane() * (size_t)T;
+    int st;
+    if ((st = ensure(ctx, ctx->vL, tab_bytes)) || (st = ensure(ctx, ctx->hL, tab_bytes)) ||
+        (st = ensure(ctx, ctx->vR, tab_bytes)) || (st = ensure(ctx, ctx->hR, tab_bytes)))
+        return st;
+    for (int i = 0; i < (tiled ? 2 : 3); i++)
+        if ((st = ensure(ctx, ctx->vol[i], vol_bytes))) return st;
+    if (tiled && r > 0 && ((st = ensure(ctx, ctx->den_v, vol_bytes)) || (st = ensure(ctx, ctx->den_h, vol_bytes)))) return st;
+    float *vL = (float*)ctx->vL.p, *hL = (float*)ctx->hL.p, *vR = (float*)ctx->vR.p, *hR = (float*)ctx->hR.p;
+
+    ctx->launches = 0;
+    ctx->final_volume = nullptr;
+    StageTimes t{EvTimer{ctx, tm != nullptr}};
+    t.pass_marks = r <= 24;
+    t.e_start = t.et.mark();
+    const float* fin = nullptr;
+    if (tiled) {
+        float *va = (float*)ctx->vol[0].p, *vb = (float*)ctx->vol[1].p;
+        float *den_v = (float*)ctx->den_v.p, *den_h = (float*)ctx->den_h.p;
+        cudaStream_t s = ctx->stream;
+        CUL(launch_raw_t(s, dl, dr, b, ya, yb, D, p->trunc, va));
+        t.e_raw = t.et.mark();
+        CUL(launch_support_t(s, true, dl, b, ya, yb, p->gamma_c, p->gamma_p, vL));
+        CUL(launch_support_t(s, false, dl, b, ya, yb, p->gamma_c, p->gamma_p, hL));
+        CUL(launch_support_t(s, true, dr, b, ya, yb, p->gamma_c, p->gamma_p, vR));
+        CUL(launch_support_t(s, false, dr, b, ya, yb, p->gamma_c, p->gamma_p, hR));
+        t.e_supp = t.et.mark();
+        // V reads va, writes vb; H reads vb, writes va (its input was consumed by V already).
+        for (int it = 0; it < r; it++) {
+            const int ylo = max(ya, y0 - (r - 1 - it) * R), yhi = min(yb, y1 + (r - 1 - it) * R);
+            CUL(launch_vagg_t(s, it == 0, b, ylo, yhi, D, vL, vR, va, den_v, vb));
+            if (t.pass_marks) t.et.mark();
+            CUL(launch_hagg_t(s, it == 0, b, ylo, yhi, D, hL, hR, vb, den_h, va));
+            if (t.pass_marks) t.et.mark();
+        }
+        t.e_agg = t.et.mark();
+        CUL(launch_wta_t(s, b, y0, y1, y0, D, va, d_rgba, d_d, d_conf));
+        t.e_wta = t.et.mark();
+        if (ctx->keep_volume) {
+            // hand the final volume out in the reference layout (x + W*y + W*rows*d, rows = y1-y0)
+            if ((st = ensure(ctx, ctx->vol_ref, sizeof(float) * (size_t)W * (y1 - y0) * D))) return st;
+            CUL(launch_volume_to_ref(s, b, y0, y1, D, va, (float*)ctx->vol_ref.p));
+            fin = (const float*)ctx->vol_ref.p;
+        }
+    } else {
+        float *raw = (float*)ctx->vol[0].p, *va = (float*)ctx->vol[1].p, *hb = (float*)ctx->vol[2].p;
+        if ((st = launch_raw(ctx, dl, dr, b, ya, yb, p, raw))) return st;                 // main.cpp:463-466
+        t.e_raw = t.et.mark();
+        if ((st = launch_support(ctx, true, dl, b, ya, yb, p, vL))) return st;            // main.cpp:470-472
+        if ((st = launch_support(ctx, false, dl, b, ya, yb, p, hL))) return st;           // :474-476
+        if ((st = launch_support(ctx, true, dr, b, ya, yb, p, vR))) return st;            // :478-480
+        if ((st = launch_support(ctx, false, dr, b, ya, yb, p, hR))) return st;           // :482-484
+        t.e_supp = t.et.mark();
+        const float* in = raw;
+        for (int it = 0; it < r; it++) {                                                  // main.cpp:492-515
+            const int ylo = max(ya, y0 - (r - 1 - it) * R), yhi = min(yb, y1 + (r - 1 - it) * R);
+            if ((st = launch_agg_basic(ctx, true, b, ylo, yhi, p, vL, vR, in, nullptr, va))) return st;
+            if (t.pass_marks) t.et.mark();
+            if ((st = launch_agg_basic(ctx, false, b, ylo, yhi, p, hL, hR, va, nullptr, hb))) return st;
+            if (t.pass_marks) t.et.mark();
+            in = hb;
+        }
+        t.e_agg = t.et.mark();
+        if ((st = launch_wta(ctx, b, y0, y1, y0, p, in, d_rgba, d_d, nullptr, nullptr, nullptr, d_conf, nullptr))) return st;  // main.cpp:519-526
+        t.e_wta = t.et.mark();
+        if (ctx->keep_volume) {
+            // band-local rows [ya,yb) -> hand out rows [y0,y1) only when the band is the whole buffer
+            if (ya == y0 && yb == y1) fin = in;
+            else {
+                if ((st = ensure(ctx, ctx->vol_ref, sizeof(float) * (size_t)W * (y1 - y0) * D))) return st;
+                for (int d = 0; d < D; d++)
+                    CU(cudaMemcpyAsync((float*)ctx->vol_ref.p + (size_t)d * W * (y1 - y0), in + (size_t)d * b.plane() + (size_t)(y0 - ya) * W,
+                                       sizeof(float) * (size_t)W * (y1 - y0), cudaMemcpyDeviceToDevice, ctx->stream));
+                fin = (const float*)ctx->vol_ref.p;
+            }
+        }
+    }
+    ctx->final_volume = fin;
+    if (tm) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        t.fill(tm, r, ctx->launches);
+    }
+    return ASW_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* asw_version(void) { return "asw_b200 0.1 (sm_100a)"; }
+
+const char* asw_strerror(int s) {
+    switch (s) {
+        case ASW_OK: return "ok";
+        case ASW_ERR_INVALID: return "invalid argument";
+        case ASW_ERR_CUDA: return "CUDA runtime error";
+        case ASW_ERR_NOMEM: return "out of memory";
+        case ASW_ERR_UNSUPPORTED: return "unsupported parameter";
+        default: return "unknown status";
+    }
+}
+
+void asw_params_default(asw_params* p) {
+    if (!p) return;
+    p->radius = 16; p->ndisp = 61; p->gamma_c = 30.91f; p->gamma_p = 28.21f; p->trunc = INFINITY; p->iterations = 7;
+}
+
+int asw_create(asw_ctx** out, int device) {
+    if (!out) return ASW_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) { cudaGetLastError(); return ASW_ERR_CUDA; }   // no GPU: fail loudly, no fallback
+    if (device < 0 || device >= n) return ASW_ERR_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return ASW_ERR_CUDA;
+    asw_ctx* ctx = new (std::nothrow) asw_ctx();
+    if (!ctx) return ASW_ERR_NOMEM;
+    ctx->device = device;
+    if (cudaGetDeviceProperties(&ctx->prop, device) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return ASW_ERR_CUDA;
+    }
+    for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+    if (tiled_configure() != cudaSuccess) { cudaGetLastError(); asw_destroy(ctx); return ASW_ERR_CUDA; }
+    *out = ctx;
+    return ASW_OK;
+}
+
+int asw_destroy(asw_ctx* ctx) {
+    if (!ctx) return ASW_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    Scratch* all[] = {&ctx->img_l, &ctx->img_r, &ctx->out_rgba, &ctx->out_d, &ctx->out_conf, &ctx->vL, &ctx->hL, &ctx->vR,
+                      &ctx->hR, &ctx->vol[0], &ctx->vol[1], &ctx->vol[2], &ctx->den_v, &ctx->den_h, &ctx->vol_ref};
+    for (Scratch* s : all) if (s->p) cudaFree(s->p);
+    for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return ASW_OK;
+}
+
+const char* asw_last_error(asw_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+void* asw_stream(asw_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int asw_sync(asw_ctx* ctx) {
+    if (!ctx) return ASW_ERR_INVALID;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return ASW_OK;
+}
+
+int asw_device_info(asw_ctx* ctx, int* sm_count, int* sm_clock_khz, size_t* total_mem, char* name, size_t name_len) {
+    if (!ctx) return ASW_ERR_INVALID;
+    if (sm_count) *sm_count = ctx->prop.multiProcessorCount;
+    if (sm_clock_khz) { int khz = 0; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device); *sm_clock_khz = khz; }
+    if (total_mem) *total_mem = ctx->prop.totalGlobalMem;
+    if (name && name_len) { strncpy(name, ctx->prop.name, name_len - 1); name[name_len - 1] = 0; }
+    return ASW_OK;
+}
+
+int asw_set_kernel_family(asw_ctx* ctx, int family) {
+    if (!ctx || family < 0 || family > 1) return ASW_ERR_INVALID;
+    ctx->family = family;
+    return ASW_OK;
+}
+
+int asw_set_keep_volume(asw_ctx* ctx, int keep) {
+    if (!ctx) return ASW_ERR_INVALID;
+    ctx->keep_volume = keep != 0;
+    return ASW_OK;
+}
+
+const float* asw_final_volume(asw_ctx* ctx) { return ctx ? ctx->final_volume : nullptr; }
+
+int asw_disparity_band_device(asw_ctx* ctx, const uint8_t* dl, const uint8_t* dr, int W, int H, int y0, int y1,
+                              const asw_params* prm, uint8_t* d_rgba, uint8_t* d_d, float* d_conf, asw_timing* tm) {
+    int st = check_params(ctx, W, H, prm);
+    if (st) return st;
+    if (!dl || !dr) return fail(ctx, ASW_ERR_INVALID, "image pointer is NULL");
+    if (y0 < 0 || y1 > H || y0 >= y1) return fail(ctx, ASW_ERR_INVALID, "band must satisfy 0 <= y0 < y1 <= H");
+    if (prm->ndisp > 256 && d_d) return fail(ctx, ASW_ERR_UNSUPPORTED, "disp_d is uint8: ndisp <= 256 required");
+    CU(cudaSetDevice(ctx->device));
+    return run_band(ctx, dl, dr, W, H, y0, y1, prm, d_rgba, d_d, d_conf, tm);
+}
+
+int asw_disparity_device(asw_ctx* ctx, const uint8_t* dl, const uint8_t* dr, int W, int H, const asw_params* prm,
+                         uint8_t* d_rgba, uint8_t* d_d, float* d_conf, asw_timing* tm) {
+    return asw_disparity_band_device(ctx, dl, dr, W, H, 0, H, prm, d_rgba, d_d, d_conf, tm);
+}
+
+int asw_disparity(asw_ctx* ctx, const uint8_t* left, const uint8_t* right, int W, int H, const asw_params* prm,
+                  uint8_t* disp_rgba, uint8_t* disp_d, float* conf, asw_timing* tm) {
+    int st = check_params(ctx, W, H, prm);
+    if (st) return st;
+    if (!left || !right) return fail(ctx, ASW_ERR_INVALID, "image pointer is NULL");
+    CU(cudaSetDevice(ctx->device));
+    const size_t npx = (size_t)W * H;
+    if ((st = ensure(ctx, ctx->img_l, npx * 4)) || (st = ensure(ctx, ctx->img_r, npx * 4))) return st;
+    if (disp_rgba && (st = ensure(ctx, ctx->out_rgba, npx * 4))) return st;
+    if (disp_d && (st = ensure(ctx, ctx->out_d, npx))) return st;
+    if (conf && (st = ensure(ctx, ctx->out_conf, npx * 4))) return st;
+    cudaEvent_t e0 = ctx->ev[asw_ctx::kMaxEvents - 1], e1 = ctx->ev[asw_ctx::kMaxEvents - 2],
+                e2 = ctx->ev[asw_ctx::kMaxEvents - 3], e3 = ctx->ev[asw_ctx::kMaxEvents - 4];
+    if (tm) cudaEventRecord(e0, ctx->stream);
+    CU(cudaMemcpyAsync(ctx->img_l.p, left, npx * 4, cudaMemcpyHostToDevice, ctx->stream));     // main.cpp:243
+    CU(cudaMemcpyAsync(ctx->img_r.p, right, npx * 4, cudaMemcpyHostToDevice, ctx->stream));    // main.cpp:244
+    if (tm) cudaEventRecord(e1, ctx->stream);
+    asw_timing inner;
+    st = asw_disparity_band_device(ctx, (const uint8_t*)ctx->img_l.p, (const uint8_t*)ctx->img_r.p, W, H, 0, H, prm,
+                                   disp_rgba ? (uint8_t*)ctx->out_rgba.p : nullptr, disp_d ? (uint8_t*)ctx->out_d.p : nullptr,
+                                   conf ? (float*)ctx->out_conf.p : nullptr, tm ? &inner : nullptr);
+    if (st) return st;
+    if (tm) cudaEventRecord(e2, ctx->stream);
+    if (disp_rgba) CU(cudaMemcpyAsync(disp_rgba, ctx->out_rgba.p, npx * 4, cudaMemcpyDeviceToHost, ctx->stream));  // main.cpp:621
+    if (disp_d) CU(cudaMemcpyAsync(disp_d, ctx->out_d.p, npx, cudaMemcpyDeviceToHost, ctx->stream));
+    if (conf) CU(cudaMemcpyAsync(conf, ctx->out_conf.p, npx * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (tm) cudaEventRecord(e3, ctx->stream);
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (tm) {
+        *tm = inner;
+        cudaEventElapsedTime(&tm->h2d_ms, e0, e1);
+        cudaEventElapsedTime(&tm->d2h_ms, e2, e3);
+    }
+    return ASW_OK;
+}
+
+// ---- per-operator entry points -----------------------------------------------------------
+#define OP_PROLOGUE(ptr_ok)                                               \
+    int st = check_params(ctx, W, H, prm);                                \
+    if (st) return st;                                                    \
+    if (!(ptr_ok)) return fail(ctx, ASW_ERR_INVALID, "device pointer is NULL"); \
+    CU(cudaSetDevice(ctx->device));                                       \
+    Band b{W, H, 0, H};
+
+int asw_Aggr(asw_ctx* ctx, const uint8_t* l, const uint8_t* r, int W, int H, const asw_params* prm, float* cost) {
+    OP_PROLOGUE(l && r && cost)
+    return launch_raw(ctx, l, r, b, 0, H, prm, cost);
+}
+
+int asw_vSupport(asw_ctx* ctx, const uint8_t* img, int W, int H, const asw_params* prm, float* out) {
+    OP_PROLOGUE(img && out)
+    return launch_support(ctx, true, img, b, 0, H, prm, out);
+}
+
+int asw_hSupport(asw_ctx* ctx, const uint8_t* img, int W, int H, const asw_params* prm, float* out) {
+    OP_PROLOGUE(img && out)
+    return launch_support(ctx, false, img, b, 0, H, prm, out);
+}
+
+int asw_vCostAggregation(asw_ctx* ctx, int W, int H, const asw_params* prm, const float* sl, const float* sr,
+                         const float* cin, float* den, float* cout) {
+    OP_PROLOGUE(sl && sr && cin && cout)
+    return launch_agg_basic(ctx, true, b, 0, H, prm, sl, sr, cin, den, cout);
+}
+
+int asw_hCostAggregation(asw_ctx* ctx, int W, int H, const asw_params* prm, const float* sl, const float* sr,
+                         const float* vcost, const float* denom_v, float* cout) {
+    (void)denom_v;  // accepted and ignored, as in asw_hcost_aggregation.cl:17
+    OP_PROLOGUE(sl && sr && vcost && cout)
+    return launch_agg_basic(ctx, false, b, 0, H, prm, sl, sr, vcost, nullptr, cout);
+}
+
+int asw_WTA(asw_ctx* ctx, int W, int H, const asw_params* prm, const float* cost, uint8_t* out_rgba, float* d_ref,
+            float* d_tar, uint8_t* out_tar_rgba, float* conf_ref, float* conf_tar) {
+    OP_PROLOGUE(cost)
+    return launch_wta(ctx, b, 0, H, 0, prm, cost, out_rgba, nullptr, d_ref, d_tar, out_tar_rgba, conf_ref, conf_tar);
+}
+
+// ---- memory helpers --------------------------------------------------------------------------
+int asw_dev_alloc(asw_ctx* ctx, void** p, size_t bytes) {
+    if (!ctx || !p) return ASW_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    cudaError_t e = cudaMalloc(p, bytes ? bytes : 1);
+    if (e != cudaSuccess) { *p = nullptr; cudaGetLastError(); return fail(ctx, ASW_ERR_NOMEM, "cudaMalloc", e); }
+    return ASW_OK;
+}
+
+int asw_dev_free(asw_ctx* ctx, void* p) {
+    if (!ctx) return ASW_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaFree(p));
+    return ASW_OK;
+}
+
+int asw_memcpy_h2d(asw_ctx* ctx, void* d, const void* h, size_t bytes) {
+    if (!ctx || (!d && bytes) || (!h && bytes)) return ASW_ERR_INVALID;
+    CU(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return ASW_OK;
+}
+
+int asw_memcpy_d2h(asw_ctx* ctx, void* h, const void* d, size_t bytes) {
+    if (!ctx || (!d && bytes) || (!h && bytes)) return ASW_ERR_INVALID;
+    CU(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return ASW_OK;
+}
+
+int asw_host_alloc(asw_ctx* ctx, void** p, size_t bytes) {
+    if (!ctx || !p) return ASW_ERR_INVALID;
+    cudaError_t e = cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) { *p = nullptr; cudaGetLastError(); return fail(ctx, ASW_ERR_NOMEM, "cudaHostAlloc", e); }
+    return ASW_OK;
+}
+
+int asw_host_free(asw_ctx* ctx, void* p) {
+    if (!ctx) return ASW_ERR_INVALID;
+    CU(cudaFreeHost(p));
+    return ASW_OK;
+}
+
+}  // extern "C"

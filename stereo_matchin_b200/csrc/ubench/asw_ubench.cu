@@ -1,0 +1,152 @@
+// asw_ubench.cu -- measurement helpers, built as a separate library (libasw_ubench.so).
+// Not part of the drop-in ABI: bench.py uses asw_ubench_ffma_tflops() to calibrate the FP32
+// roofline denominator on the GPU it runs on (MEASURED_PEAKS.json only holds HBM and bf16),
+// and the other probes document the shared-memory / packed-FP32 behaviour the tiled kernels
+// were designed around (profiles/).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define UB_API extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+template <int ILP>
+__global__ void k_ffma(float* out, int iters, float a, float b) {
+    float acc[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; i++) acc[i] = threadIdx.x * 0.001f + i;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < ILP; i++) acc[i] = __fmaf_rn(acc[i], a, b);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < ILP; i++) s += acc[i];
+    if (s == 123.456f) out[0] = s;
+}
+
+// packed FP32: fma.rn.f32x2 (SASS FFMA2) on 64-bit register pairs
+template <int ILP>
+__global__ void k_ffma2(float* out, int iters, float a, float b) {
+    unsigned long long acc[ILP], va, vb;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(va) : "f"(a));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(vb) : "f"(b));
+#pragma unroll
+    for (int i = 0; i < ILP; i++) {
+        float x = threadIdx.x * 0.001f + i;
+        asm("mov.b64 %0, {%1, %1};" : "=l"(acc[i]) : "f"(x));
+    }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < ILP; i++) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(acc[i]) : "l"(va), "l"(vb));
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < ILP; i++) {
+        float lo, hi;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[i]));
+        s += lo + hi;
+    }
+    if (s == 123.456f) out[0] = s;
+}
+
+// mix: per `ILP` FFMA, one LDS.128 with the given address pattern
+//   mode 0: all lanes distinct (conflict-free), 1: all lanes same address (broadcast),
+//   2: four distinct addresses (one per quarter warp), 3: eight distinct (one per 4 lanes)
+template <int FMA_PER_LDS>
+__global__ void k_lds_mix(float* out, int iters, int mode) {
+    __shared__ float4 buf[1024];
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) buf[i] = make_float4(i, 1.f, 2.f, 3.f);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int idx;
+    if (mode == 0) idx = lane;
+    else if (mode == 1) idx = 0;
+    else if (mode == 2) idx = lane >> 3;
+    else idx = lane >> 2;
+    idx += warp * 32;
+    float acc[FMA_PER_LDS > 0 ? FMA_PER_LDS : 1];
+#pragma unroll
+    for (int i = 0; i < (FMA_PER_LDS > 0 ? FMA_PER_LDS : 1); i++) acc[i] = lane + i;
+    float4 s4 = make_float4(0, 0, 0, 0);
+    for (int it = 0; it < iters; it++) {
+        float4 v;
+        const unsigned addr = (unsigned)__cvta_generic_to_shared(&buf[(idx + it * 32) & 1023]);
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+        s4.x += v.x + v.w;   // keep the load alive
+#pragma unroll
+        for (int i = 0; i < FMA_PER_LDS; i++) acc[i] = __fmaf_rn(acc[i], 1.0001f, v.y);
+    }
+    float s = s4.x;
+#pragma unroll
+    for (int i = 0; i < (FMA_PER_LDS > 0 ? FMA_PER_LDS : 1); i++) s += acc[i];
+    if (s == 123.456f) out[0] = s;
+}
+
+float time_ms(void (*launch)(void*), void* arg, int reps) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    launch(arg);
+    cudaDeviceSynchronize();
+    float best = 1e30f;
+    for (int r = 0; r < reps; r++) {
+        cudaEventRecord(a);
+        launch(arg);
+        cudaEventRecord(b);
+        cudaEventSynchronize(b);
+        float ms;
+        cudaEventElapsedTime(&ms, a, b);
+        if (ms < best) best = ms;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    return best;
+}
+
+struct Arg {
+    float* out;
+    int iters, blocks, threads, mode;
+};
+
+}  // namespace
+
+// Sustained FP32 FMA throughput in TFLOP/s (2 flop per FMA), dependent chains with ILP 8.
+UB_API double asw_ubench_ffma_tflops(int packed) {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    Arg a{nullptr, 4096, sms * 8, 256, 0};
+    cudaMalloc(&a.out, 64);
+    float ms;
+    if (packed) ms = time_ms([](void* p) { Arg* a = (Arg*)p; k_ffma2<8><<<a->blocks, a->threads>>>(a->out, a->iters, 1.0001f, 0.5f); }, &a, 5);
+    else ms = time_ms([](void* p) { Arg* a = (Arg*)p; k_ffma<8><<<a->blocks, a->threads>>>(a->out, a->iters, 1.0001f, 0.5f); }, &a, 5);
+    cudaFree(a.out);
+    if (cudaGetLastError() != cudaSuccess) return -1.0;
+    double fmas = (double)a.blocks * a.threads * a.iters * 8 * (packed ? 2 : 1);
+    return 2.0 * fmas / (ms * 1e-3) / 1e12;
+}
+
+// Shared-memory probe: returns SM-cycles-equivalent: LDS.128 warp-instructions per ns per SM
+// for the address pattern `mode` with `fma_per_lds` FFMAs between loads (0, 4, 8, 16).
+UB_API double asw_ubench_lds(int mode, int fma_per_lds, double* out_ms) {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    Arg a{nullptr, 8192, sms * 4, 512, mode};
+    cudaMalloc(&a.out, 64);
+    float ms = -1.f;
+    switch (fma_per_lds) {
+        case 0: ms = time_ms([](void* p) { Arg* a = (Arg*)p; k_lds_mix<0><<<a->blocks, a->threads>>>(a->out, a->iters, a->mode); }, &a, 5); break;
+        case 4: ms = time_ms([](void* p) { Arg* a = (Arg*)p; k_lds_mix<4><<<a->blocks, a->threads>>>(a->out, a->iters, a->mode); }, &a, 5); break;
+        case 8: ms = time_ms([](void* p) { Arg* a = (Arg*)p; k_lds_mix<8><<<a->blocks, a->threads>>>(a->out, a->iters, a->mode); }, &a, 5); break;
+        case 16: ms = time_ms([](void* p) { Arg* a = (Arg*)p; k_lds_mix<16><<<a->blocks, a->threads>>>(a->out, a->iters, a->mode); }, &a, 5); break;
+        default: break;
+    }
+    cudaFree(a.out);
+    if (ms < 0 || cudaGetLastError() != cudaSuccess) return -1.0;
+    if (out_ms) *out_ms = ms;
+    double lds = (double)a.blocks * (a.threads / 32) * a.iters;  // warp-level LDS.128 instructions
+    return lds / (ms * 1e6) / sms;                                // per ns per SM
+}

@@ -1,0 +1,283 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the
+same inputs.  Bar (north_star): integer / index outputs identical; aggregated costs within
+1e-5 relative of the reference arithmetic.  Because the oracle's FMA variant (use_fma=True)
+performs exactly the operations the kernels perform, in the same order, the comparison
+against it is BIT-EXACT for every float as well; the 1e-5 / tie-flip accounting is done
+against the separately-rounded variant (use_fma=False), the other arithmetic the
+reference's OpenCL build may legally produce.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, crop_pair, load_pair, load_rgba
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-5          # north_star: aggregated costs within 1e-5 relative
+MAX_FLIP_FRACTION = 1e-3  # north_star: <= 0.1 % tie-flip pixels
+
+
+def P(**kw):
+    from stereo_matchin_b200.api import AswParams
+    return AswParams(**kw)
+
+
+def OP(p):
+    from oracle.asw_oracle import OracleParams
+    return OracleParams(p.radius, p.ndisp, p.gamma_c, p.gamma_p, p.trunc, p.iterations)
+
+
+def run_fused(ctx, L, R, p, family=0, keep=False, band=None):
+    """asw_disparity_device / asw_disparity_band_device on uploaded images -> numpy outputs."""
+    H, W, _ = L.shape
+    y0, y1 = band if band else (0, H)
+    rows = y1 - y0
+    ctx.set_kernel_family(family)
+    ctx.set_keep_volume(keep)
+    dl, dr = ctx.to_device(L), ctx.to_device(R)
+    o_rgba, o_d, o_conf = ctx.alloc(rows * W * 4), ctx.alloc(rows * W), ctx.alloc(rows * W * 4)
+    ctx.disparity_raw(dl.ptr, dr.ptr, W, H, p, o_rgba.ptr, o_d.ptr, o_conf.ptr, band=band)
+    ctx.sync()
+    out = {"left": o_rgba.download((rows, W, 4), np.uint8), "d": o_d.download((rows, W), np.uint8),
+           "conf": o_conf.download((rows, W), np.float32)}
+    if keep:
+        ptr = ctx.final_volume_ptr()
+        assert ptr, "final volume was not kept"
+        cost = np.empty((p.ndisp, rows, W), np.float32)
+        ctx._check(ctx.lib.asw_memcpy_d2h(ctx.h, cost.ctypes.data, ptr, cost.nbytes))
+        out["cost"] = cost
+    ctx.set_kernel_family(0)
+    ctx.set_keep_volume(False)
+    for b in (dl, dr, o_rgba, o_d, o_conf):
+        b.free()
+    return out
+
+
+def assert_bit_equal(a, b, what):
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    assert a.shape == b.shape, what
+    if a.dtype == np.float32:
+        ok = a.view(np.uint32) == b.view(np.uint32)
+    else:
+        ok = a == b
+    if not ok.all():
+        idx = np.argwhere(~ok)
+        i = tuple(idx[0])
+        raise AssertionError(f"{what}: {len(idx)} of {a.size} elements differ; first at {i}: {a[i]!r} vs {b[i]!r}")
+
+
+# ---------------------------------------------------------------------------------------------
+# per-operator parity (reference layouts, device pointers)
+
+OP_CASES = [("teddy", 0, 0, 96, 40, 61), ("cones", 300, 200, 150, 37, 61), ("tsukuba", 0, 0, 384, 60, 16),
+            ("art", 10, 10, 33, 70, 5), ("laundry", 440, 0, 10, 50, 9), ("teddy", 7, 9, 1, 35, 3),
+            ("teddy", 7, 9, 35, 1, 3), ("cones", 0, 0, 70, 70, 1)]
+
+
+@pytest.mark.parametrize("ds,x0,y0,w,h,D", OP_CASES)
+def test_operator_parity(ctx, oracle, ds, x0, y0, w, h, D):
+    L, R = crop_pair(ds, x0, y0, w, h)
+    p = P(ndisp=D)
+    T, n = 33, w * h
+    dl, dr = ctx.to_device(L), ctx.to_device(R)
+
+    cost = ctx.alloc(4 * n * D)
+    ctx.asw_Aggr(dl.ptr, dr.ptr, w, h, p, cost.ptr)                              # asw_aggr.cl
+    raw = cost.download((D, h, w), np.float32)
+    assert_bit_equal(raw, oracle.asw_aggr(L, R, D), "asw_Aggr")
+
+    tabs, otabs = {}, {}
+    for name, img, dimg, vert in (("vl", L, dl, True), ("hl", L, dl, False), ("vr", R, dr, True), ("hr", R, dr, False)):
+        tabs[name] = ctx.alloc(4 * n * T)
+        (ctx.asw_vSupport if vert else ctx.asw_hSupport)(dimg.ptr, w, h, p, tabs[name].ptr)   # asw_vsupport.cl / asw_hsupport.cl
+        otabs[name] = oracle.asw_support(img, vert)
+        assert_bit_equal(tabs[name].download((T, h, w), np.float32), otabs[name], f"support {name}")
+
+    vout, vden, hout = ctx.alloc(4 * n * D), ctx.alloc(4 * n * D), ctx.alloc(4 * n * D)
+    ctx.asw_vCostAggregation(w, h, p, tabs["vl"].ptr, tabs["vr"].ptr, cost.ptr, vden.ptr, vout.ptr)
+    ov, oden = oracle.asw_vcost_aggregation(otabs["vl"], otabs["vr"], raw, use_fma=True)
+    assert_bit_equal(vout.download((D, h, w), np.float32), ov, "asw_vCostAggregation cost")
+    assert_bit_equal(vden.download((D, h, w), np.float32), oden, "asw_vCostAggregation denom")
+    ctx.asw_hCostAggregation(w, h, p, tabs["hl"].ptr, tabs["hr"].ptr, vout.ptr, vden.ptr, hout.ptr)
+    oh = oracle.asw_hcost_aggregation(otabs["hl"], otabs["hr"], ov, use_fma=True)
+    assert_bit_equal(hout.download((D, h, w), np.float32), oh, "asw_hCostAggregation")
+    # against the separately rounded arithmetic: within the north_star tolerance
+    oh0 = oracle.asw_hcost_aggregation(otabs["hl"], otabs["hr"],
+                                       oracle.asw_vcost_aggregation(otabs["vl"], otabs["vr"], raw, use_fma=False)[0], use_fma=False)
+    assert np.allclose(hout.download((D, h, w), np.float32), oh0, rtol=REL_TOL, atol=0)
+
+    o_l, o_r = ctx.alloc(4 * n), ctx.alloc(4 * n)
+    f = [ctx.alloc(4 * n) for _ in range(4)]
+    ctx.asw_WTA(w, h, p, hout.ptr, o_l.ptr, f[0].ptr, f[1].ptr, o_r.ptr, f[2].ptr, f[3].ptr)    # asw_wta.cl
+    ow = oracle.asw_wta(oh, right_view=True)
+    assert_bit_equal(o_l.download((h, w, 4), np.uint8), ow["left"], "WTA left image")
+    assert_bit_equal(o_r.download((h, w, 4), np.uint8), ow["right"], "WTA right image")
+    for buf, key in zip(f, ("d_ref", "d_tar", "conf_ref", "conf_tar")):
+        assert_bit_equal(buf.download((h, w), np.float32), ow[key], f"WTA {key}")
+
+
+# ---------------------------------------------------------------------------------------------
+# fused hot path, both kernel families, bundled pairs
+
+@pytest.mark.parametrize("family", [0, 1], ids=["tiled", "basic"])
+@pytest.mark.parametrize("ds,D", [("tsukuba", 61), ("teddy", 61), ("cones", 61), ("sukub", 16)])
+def test_fused_parity_bundled_pairs(ctx, oracle, ds, D, family):
+    L, R = load_pair(ds)
+    p = P(ndisp=D)
+    g = run_fused(ctx, L, R, p, family=family, keep=True)
+    o = oracle.asw_hot_path(L, R, OP(p), use_fma=True, want_cost=True)
+    assert_bit_equal(g["cost"], o["cost"], "final aggregated volume")
+    assert_bit_equal(g["left"], o["left"], "disparity image")
+    assert_bit_equal(g["d"].astype(np.float32), o["d_ref"], "disparity index")
+    assert_bit_equal(g["conf"], o["conf_ref"], "confidence")
+    # vs the reference's other legal arithmetic (no FMA): costs within 1e-5, flips counted
+    o0 = oracle.asw_hot_path(L, R, OP(p), use_fma=False, want_cost=True)
+    rel = np.abs(g["cost"] - o0["cost"]) / np.maximum(np.abs(o0["cost"]), 1e-30)
+    assert rel.max() <= REL_TOL, f"max relative cost error {rel.max():.3g}"
+    flips = g["d"].astype(np.float32) != o0["d_ref"]
+    assert flips.mean() <= MAX_FLIP_FRACTION, f"{flips.sum()} disparity flips vs the no-FMA oracle"
+    if flips.any():   # every flip must be a near-tie of the reference's two candidates
+        ys, xs = np.nonzero(flips)
+        c = o0["cost"]
+        gap = np.abs(c[g["d"][ys, xs], ys, xs] - c[o0["d_ref"][ys, xs].astype(int), ys, xs])
+        assert (gap / c.min(0)[ys, xs]).max() <= REL_TOL
+
+
+@pytest.mark.parametrize("ds", ["tsukuba", "teddy", "cones", "art", "laundry"])
+def test_fused_vs_reference_golden_png(ctx, oracle, ds):
+    """Left WTA disparity vs the reference's committed asw_consistency_pre-reff.png on the
+    pixels the reference marked consistent; tsukuba is byte-exact, the rest up to tie flips
+    in the clamped band x < 61 (same bound as the oracle pin, tests/test_oracle_golden.py)."""
+    L, R = load_pair(ds)
+    g = run_fused(ctx, L, R, P())
+    gold = load_rgba(os.path.join(GOLDEN, ds, "asw_consistency_pre-reff.png"))
+    red = (gold[..., 0] == 255) & (gold[..., 1] == 0) & (gold[..., 2] == 0)
+    mism = (~red) & (gold[..., 0] != g["left"][..., 0])
+    limit = {"tsukuba": 0, "teddy": 120, "cones": 160, "art": 420, "laundry": 30}[ds]
+    assert mism.sum() <= limit
+    if mism.any():
+        assert np.nonzero(mism)[1].max() < 61
+
+
+# ---------------------------------------------------------------------------------------------
+# edge cases: ragged sizes, extreme parameters
+
+EDGE = [  # (W, H, D, iterations)
+    (1, 1, 1, 1), (1, 40, 4, 2), (40, 1, 4, 2), (5, 7, 3, 7), (33, 33, 33, 2), (63, 20, 32, 1), (65, 18, 61, 1),
+    (130, 17, 100, 1), (70, 35, 256, 1), (129, 9, 200, 2), (64, 64, 16, 0), (50, 20, 61, 3),
+]
+
+
+@pytest.mark.parametrize("W,H,D,it", EDGE)
+@pytest.mark.parametrize("family", [0, 1], ids=["tiled", "basic"])
+def test_fused_edge_shapes(ctx, oracle, W, H, D, it, family):
+    rng = np.random.default_rng(W * 1000 + H * 10 + D)
+    L = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
+    R = np.roll(L, -3, axis=1) if W > 4 else rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
+    R = np.ascontiguousarray(R)
+    R[..., :3] = np.clip(R[..., :3].astype(int) + rng.integers(-6, 7, (H, W, 3)), 0, 255).astype(np.uint8)
+    p = P(ndisp=D, iterations=it)
+    g = run_fused(ctx, L, R, p, family=family, keep=True)
+    o = oracle.asw_hot_path(L, R, OP(p), use_fma=True, want_cost=True)
+    assert_bit_equal(g["cost"], o["cost"], "final aggregated volume")
+    assert_bit_equal(g["d"].astype(np.float32), o["d_ref"], "disparity index")
+    assert_bit_equal(g["left"], o["left"], "disparity image")
+    assert_bit_equal(g["conf"], o["conf_ref"], "confidence")
+
+
+def test_trunc_and_other_radius(ctx, oracle):
+    """trunc caps the raw cost; a radius other than 16 runs on the generic CUDA kernels."""
+    L, R = crop_pair("teddy", 100, 100, 90, 50)
+    for p in (P(ndisp=20, trunc=40.0, iterations=2), P(ndisp=12, radius=3, iterations=2), P(ndisp=12, radius=0, iterations=1),
+              P(ndisp=24, gamma_c=10.0, gamma_p=5.0, iterations=1)):
+        g = run_fused(ctx, L, R, p, keep=True)
+        o = oracle.asw_hot_path(L, R, OP(p), use_fma=True, want_cost=True)
+        assert_bit_equal(g["cost"], o["cost"], f"volume {p}")
+        assert_bit_equal(g["d"].astype(np.float32), o["d_ref"], f"disparity {p}")
+
+
+def test_known_answers(ctx):
+    """Oracle-independent checks: a constant pair has all-equal costs (d = 0, confidence 0); a
+    right image shifted by k pixels yields d = k away from the borders."""
+    H, W, D, k = 48, 160, 32, 7
+    const = np.full((H, W, 4), 200, np.uint8)
+    g = run_fused(ctx, const, const, P(ndisp=D, iterations=2))
+    assert not g["d"].any() and not g["conf"].any() and np.all(g["left"][..., :3] == 0) and np.all(g["left"][..., 3] == 255)
+    rng = np.random.default_rng(0)
+    L = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
+    R = np.empty_like(L)
+    R[:, : W - k] = L[:, k:]
+    R[:, W - k:] = L[:, -1:]
+    g = run_fused(ctx, L, R, P(ndisp=D, iterations=2))
+    assert np.all(g["d"][:, D + 16: W - 16] == k)
+
+
+# ---------------------------------------------------------------------------------------------
+# row bands (the multi-GPU sharding unit) and host-buffer entry point
+
+def test_band_equals_full_frame(ctx):
+    L, R = load_pair("teddy")
+    H = L.shape[0]
+    p = P(ndisp=61, iterations=3)
+    full = run_fused(ctx, L, R, p)
+    for (y0, y1) in [(0, 50), (50, 51), (100, 260), (300, H), (H - 1, H)]:
+        b = run_fused(ctx, L, R, p, band=(y0, y1))
+        assert_bit_equal(b["d"], full["d"][y0:y1], f"band {y0}:{y1} disparity")
+        assert_bit_equal(b["conf"], full["conf"][y0:y1], f"band {y0}:{y1} confidence")
+        assert_bit_equal(b["left"], full["left"][y0:y1], f"band {y0}:{y1} image")
+
+
+def test_host_entry_point_and_timing(ctx, oracle):
+    L, R = load_pair("tsukuba")
+    p = P()
+    out = ctx.disparity(L, R, p, want_timing=True)
+    o = oracle.asw_hot_path(L, R, OP(p), use_fma=True)
+    assert_bit_equal(out["disp_rgba"], o["left"], "asw_disparity image")
+    assert_bit_equal(out["conf"], o["conf_ref"], "asw_disparity confidence")
+    t = out["timing"]
+    assert t["total_ms"] > 0 and t["agg_total_ms"] > 0 and t["kernel_launches"] >= 2 * p.iterations + 1
+    assert t["h2d_ms"] > 0 and t["d2h_ms"] > 0
+    assert t["agg_total_ms"] <= t["total_ms"] * 1.001
+
+
+def test_error_behaviour(ctx):
+    """Bad arguments return status codes (never crash, never fall back)."""
+    from stereo_matchin_b200.api import AswError, ASW_ERR_INVALID, ASW_ERR_UNSUPPORTED
+    L, R = crop_pair("teddy", 0, 0, 32, 16)
+    for bad, code in ((P(ndisp=0), ASW_ERR_INVALID), (P(radius=-1), ASW_ERR_INVALID), (P(gamma_c=0.0), ASW_ERR_INVALID),
+                      (P(radius=65), ASW_ERR_UNSUPPORTED), (P(iterations=-1), ASW_ERR_INVALID)):
+        with pytest.raises(AswError) as e:
+            ctx.disparity(L, R, bad)
+        assert e.value.status == code
+    with pytest.raises(AswError):
+        ctx.disparity_raw(0, 0, 32, 16, P(), None, None, None)
+    with pytest.raises(AswError):
+        dl = ctx.to_device(L)
+        ctx.disparity_raw(dl.ptr, dl.ptr, 32, 16, P(), None, None, None, band=(5, 5))
+    assert ctx.disparity(L, R, P(ndisp=8))["disp_d"].shape == (16, 32)   # context still usable afterwards
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json full size (cfg3: 1800 x 1500, 256 disparities) through size-independent properties
+
+def test_full_size_cfg3_properties(ctx, oracle):
+    from stereo_matchin_b200.synth import make_config
+    L, R, _, D = make_config("cfg3_1800x1500_d256")
+    H, W, _ = L.shape
+    p = P(ndisp=D)
+    full = run_fused(ctx, L, R, p)
+    # (1) a row band computed through the halo-shrinking band entry equals the same rows of the frame
+    b = run_fused(ctx, L, R, p, band=(700, 716))
+    assert_bit_equal(b["d"], full["d"][700:716], "cfg3 band disparity")
+    assert_bit_equal(b["conf"], full["conf"][700:716], "cfg3 band confidence")
+    # (2) the same band from the CPU oracle run on the rows that can influence it (r*R = 112 halo rows)
+    ya, yb = 700 - 112, 716 + 112
+    o = oracle.asw_hot_path(np.ascontiguousarray(L[ya:yb]), np.ascontiguousarray(R[ya:yb]), OP(p), use_fma=True)
+    assert_bit_equal(full["d"][700:716].astype(np.float32), o["d_ref"][112:128], "cfg3 band vs oracle: disparity")
+    assert_bit_equal(full["conf"][700:716], o["conf_ref"][112:128], "cfg3 band vs oracle: confidence")
+    # (3) the two CUDA kernel families agree bit for bit on a band at full width and full D
+    b1 = run_fused(ctx, L, R, p, family=1, band=(1484, 1500))
+    assert_bit_equal(b1["d"], full["d"][1484:1500], "cfg3 tiled vs basic kernels")
+    assert_bit_equal(b1["conf"], full["conf"][1484:1500], "cfg3 tiled vs basic kernels (confidence)")
