@@ -1,0 +1,15 @@
+"""Runs the measurement probes of libasw_ubench.so and prints a small JSON report."""
+import ctypes as C, json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ub = C.CDLL(os.path.join(ROOT, "stereo_matchin_b200", "libasw_ubench.so"))
+ub.asw_ubench_ffma_tflops.restype = C.c_double
+ub.asw_ubench_lds.restype = C.c_double
+ub.asw_ubench_lds.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
+rep = {"ffma_tflops": ub.asw_ubench_ffma_tflops(0), "ffma2_tflops": ub.asw_ubench_ffma_tflops(1), "lds128": {}}
+names = {0: "distinct", 1: "broadcast", 2: "4_addr_quarter_warp", 3: "8_addr"}
+for mode in range(4):
+    for f in (0, 4, 8, 16):
+        ms = C.c_double()
+        v = ub.asw_ubench_lds(mode, f, C.byref(ms))
+        rep["lds128"][f"{names[mode]}_fma{f}"] = {"lds_per_ns_per_sm": v, "ms": ms.value}
+print(json.dumps(rep, indent=1))

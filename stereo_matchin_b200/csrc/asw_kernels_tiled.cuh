@@ -17,6 +17,8 @@
 //
 // Kernels are specialised for the reference's window (radius 16, 33 taps).
 #pragma once
+#include <stdlib.h>
+
 #include "asw_common.cuh"
 
 namespace asw {
@@ -103,27 +105,40 @@ __global__ void __launch_bounds__(256) k_vagg_t(const float* __restrict__ wL, co
     const size_t wr_row = (size_t)kT * W;
     const size_t crow = (size_t)W * Dp;
 
+    // All global loads of a step are issued up front (tap indices clamped so every address is
+    // valid), the next step's loads are in flight while this step's FMAs run.
+    float cj[NJ], wr[NY];
+    auto load_step = [&](int s, float (&c)[NJ], float (&r)[NY]) {
+        const int yy = clampi(clampi(y0 - kR + s, 0, b.H - 1) - b.y_off, 0, b.Hb - 1);
+#pragma unroll
+        for (int j = 0; j < NJ; j++) c[j] = __ldg(cin + (size_t)yy * crow + coff[j]);
+#pragma unroll
+        for (int k = 0; k < NY; k++)
+            r[k] = __ldg(wRp + (size_t)min(k, kmax) * wr_row + (size_t)clampi(s - k, 0, kT - 1) * W);
+    };
+    load_step(0, cj, wr);
 #pragma unroll 1
     for (int s = 0; s < NY + 2 * kR; s++) {
-        const int yy = clampi(clampi(y0 - kR + s, 0, b.H - 1) - b.y_off, 0, b.Hb - 1);
-        float cj[NJ];
-#pragma unroll
-        for (int j = 0; j < NJ; j++) cj[j] = __ldg(cin + (size_t)yy * crow + coff[j]);
+        float cn[NJ], wn[NY];
+        load_step(min(s + 1, NY + 2 * kR - 1), cn, wn);
 #pragma unroll
         for (int k = 0; k < NY; k++) {
             const int i = s - k;
             if (i >= 0 && i < kT && k <= kmax) {
-                const float wr = __ldg(wRp + (size_t)k * wr_row + (size_t)i * W);
                 const float4 wl = *reinterpret_cast<const float4*>(&sWL[(k * kT + i) * XW + NJ * w]);
                 const float wlv[4] = {wl.x, wl.y, wl.z, wl.w};
 #pragma unroll
                 for (int j = 0; j < NJ; j++) {
-                    const float ww = __fmul_rn(wlv[j], wr);
+                    const float ww = __fmul_rn(wlv[j], wr[k]);
                     acc[k][j] = __fmaf_rn(ww, cj[j], acc[k][j]);
                     if (FIRST) den[k][j] = __fadd_rn(den[k][j], ww);
                 }
             }
         }
+#pragma unroll
+        for (int j = 0; j < NJ; j++) cj[j] = cn[j];
+#pragma unroll
+        for (int k = 0; k < NY; k++) wr[k] = wn[k];
     }
 
 #pragma unroll
@@ -296,11 +311,15 @@ __global__ void k_volume_to_ref(const float* __restrict__ vol, Band b, int ylo, 
 // host-side launchers
 
 struct TiledCfg {
-    int v_ny = 16;  // output rows per thread in the vertical pass (8 or 16)
+    int v_ny = 8;  // output rows per thread in the vertical pass (8 or 16)
 };
 
 inline TiledCfg& tiled_cfg() {
-    static TiledCfg c;
+    static TiledCfg c = [] {
+        TiledCfg t;
+        if (const char* e = getenv("ASW_V_NY")) t.v_ny = atoi(e) == 16 ? 16 : 8;   // tuning knob for experiments
+        return t;
+    }();
     return c;
 }
 

@@ -199,12 +199,15 @@ def test_trunc_and_other_radius(ctx, oracle):
 
 
 def test_known_answers(ctx):
-    """Oracle-independent checks: a constant pair has all-equal costs (d = 0, confidence 0); a
-    right image shifted by k pixels yields d = k away from the borders."""
+    """Oracle-independent checks: on a constant pair every disparity has the same cost wherever
+    no tap is clamped (x >= D + R), so d = 0 wins the tie and the confidence is 0; a right image
+    shifted by k pixels yields d = k away from the borders."""
     H, W, D, k = 48, 160, 32, 7
     const = np.full((H, W, 4), 200, np.uint8)
     g = run_fused(ctx, const, const, P(ndisp=D, iterations=2))
-    assert not g["d"].any() and not g["conf"].any() and np.all(g["left"][..., :3] == 0) and np.all(g["left"][..., 3] == 255)
+    inner = slice(D + 16 * 3, W - 16 * 3)   # clamped taps (x - d < R, x > W-1-R) break the tie; each H pass spreads that by R
+    assert not g["d"][:, inner].any() and not g["conf"][:, inner].any()
+    assert np.all(g["left"][:, inner, :3] == 0) and np.all(g["left"][..., 3] == 255)
     rng = np.random.default_rng(0)
     L = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
     R = np.empty_like(L)
