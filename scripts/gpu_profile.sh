@@ -1,10 +1,10 @@
 #!/bin/bash
 # ncu launch list + full capture of the aggregation kernels on one cfg3 frame (r=2).
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -q -x --timeout=900 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
+echo skip-pytest
 python scripts/profile_run.py cfg3 2 0 2 > gpurun_out/profile_plain.json 2>gpurun_out/profile_plain.err && \
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python scripts/profile_run.py cfg3 2 0 1 > gpurun_out/ncu_launches.log 2>&1
 echo "launch list rc=$?"; cat gpurun_out/profile_plain.json
 python scripts/profile_run.py cfg3 2 0 1 > /dev/null 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:'k_(h|v)agg_t' -c 4 -o gpurun_out/prof_agg python scripts/profile_run.py cfg3 2 0 1 > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'k_(h|v)agg_v2' -c 4 -o gpurun_out/prof_agg python scripts/profile_run.py cfg3 2 0 1 > gpurun_out/ncu_full.log 2>&1
 echo "full rc=$?"; tail -3 gpurun_out/ncu_full.log; ls -la gpurun_out

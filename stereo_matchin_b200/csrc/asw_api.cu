@@ -14,6 +14,7 @@
 #include "asw_common.cuh"
 #include "asw_kernels_basic.cuh"
 #include "asw_kernels_tiled.cuh"
+#include "asw_kernels_tma.cuh"
 
 using namespace asw;
 
@@ -70,6 +71,10 @@ int ensure(asw_ctx* ctx, Scratch& s, size_t bytes) {
     cudaError_t e = cudaMalloc(&s.p, bytes);
     if (e != cudaSuccess) { s.p = nullptr; cudaGetLastError(); return fail(ctx, ASW_ERR_NOMEM, "cudaMalloc scratch", e); }
     s.cap = bytes;
+    // Zero once: padding planes / zero-weight taps may touch elements no kernel has written yet,
+    // and 0 * garbage must stay finite.  Later contents are always finite results of earlier runs.
+    e = cudaMemsetAsync(s.p, 0, bytes, ctx->stream);
+    if (e != cudaSuccess) return fail(ctx, ASW_ERR_CUDA, "cudaMemsetAsync scratch", e);
     return ASW_OK;
 }
 
@@ -183,17 +188,23 @@ int run_band(asw_ctx* ctx, const uint8_t* dl, const uint8_t* dr, int W, int H, i
     // rows whose values can influence rows [y0,y1): R rows per V pass (H passes stay in-row)
     const int ya = max(0, y0 - r * R), yb = min(H, y1 + r * R);
     Band b{W, H, ya, yb - ya};
-    const bool tiled = ctx->family == 0 && tiled_supported(R);
-    const int Dp = tiled ? padded_D(D) : D;
-    const size_t vol_bytes = sizeof(float) * b.plane() * (size_t)Dp;
+    const bool tma = ctx->family == 0 && tma_supported(R, D);
+    const bool tiled = !tma && ctx->family == 0 && tiled_supported(R);
+    const TL tl = make_tl(b, D);
+    const int Dp = (tiled || tma) ? padded_D(D) : D;
+    const size_t vol_bytes = sizeof(float) * (tma ? tl.vol_elems() : b.plane() * (size_t)Dp);
     const size_t tab_bytes = sizeof(float) * b.plane() * (size_t)T;
     int st;
-    if ((st = ensure(ctx, ctx->vL, tab_bytes)) || (st = ensure(ctx, ctx->hL, tab_bytes)) ||
-        (st = ensure(ctx, ctx->vR, tab_bytes)) || (st = ensure(ctx, ctx->hR, tab_bytes)))
+    if (tma) {
+        if ((st = ensure(ctx, ctx->vL, sizeof(float) * tl.wvl_elems())) || (st = ensure(ctx, ctx->vR, sizeof(float) * tl.wvr_elems())) ||
+            (st = ensure(ctx, ctx->hL, sizeof(float) * tl.whl_elems())) || (st = ensure(ctx, ctx->hR, sizeof(float) * tl.whr_elems())))
+            return st;
+    } else if ((st = ensure(ctx, ctx->vL, tab_bytes)) || (st = ensure(ctx, ctx->hL, tab_bytes)) ||
+               (st = ensure(ctx, ctx->vR, tab_bytes)) || (st = ensure(ctx, ctx->hR, tab_bytes)))
         return st;
-    for (int i = 0; i < (tiled ? 2 : 3); i++)
+    for (int i = 0; i < ((tiled || tma) ? 2 : 3); i++)
         if ((st = ensure(ctx, ctx->vol[i], vol_bytes))) return st;
-    if (tiled && r > 0 && ((st = ensure(ctx, ctx->den_v, vol_bytes)) || (st = ensure(ctx, ctx->den_h, vol_bytes)))) return st;
+    if ((tiled || tma) && r > 0 && ((st = ensure(ctx, ctx->den_v, vol_bytes)) || (st = ensure(ctx, ctx->den_h, vol_bytes)))) return st;
     float *vL = (float*)ctx->vL.p, *hL = (float*)ctx->hL.p, *vR = (float*)ctx->vR.p, *hR = (float*)ctx->hR.p;
 
     ctx->launches = 0;
@@ -202,7 +213,34 @@ int run_band(asw_ctx* ctx, const uint8_t* dl, const uint8_t* dr, int W, int H, i
     t.pass_marks = r <= 24;
     t.e_start = t.et.mark();
     const float* fin = nullptr;
-    if (tiled) {
+    if (tma) {
+        float *va = (float*)ctx->vol[0].p, *vb = (float*)ctx->vol[1].p;
+        float *den_v = (float*)ctx->den_v.p, *den_h = (float*)ctx->den_h.p;
+        cudaStream_t s = ctx->stream;
+        CUL(launch_raw_v2(s, dl, dr, tl, ya, yb, p->trunc, va));
+        t.e_raw = t.et.mark();
+        CUL(launch_support_v2(s, true, false, dl, tl, ya, yb, p->gamma_c, p->gamma_p, vL));
+        CUL(launch_support_v2(s, false, false, dl, tl, ya, yb, p->gamma_c, p->gamma_p, hL));
+        CUL(launch_support_v2(s, true, true, dr, tl, ya, yb, p->gamma_c, p->gamma_p, vR));
+        CUL(launch_support_v2(s, false, true, dr, tl, ya, yb, p->gamma_c, p->gamma_p, hR));
+        t.e_supp = t.et.mark();
+        for (int it = 0; it < r; it++) {
+            const int ylo = max(ya, y0 - (r - 1 - it) * R), yhi = min(yb, y1 + (r - 1 - it) * R);
+            CUL(launch_vagg_v2(s, it == 0, tl, ylo, yhi, vL, vR, va, den_v, vb));
+            ctx->launches += 2;                                // main kernel + diagonal fix-up + edge padding kernels
+            if (t.pass_marks) t.et.mark();
+            CUL(launch_hagg_v2(s, it == 0, tl, ylo, yhi, hL, hR, vb, den_h, va));
+            if (t.pass_marks) t.et.mark();
+        }
+        t.e_agg = t.et.mark();
+        CUL(launch_wta_v2(s, tl, y0, y1, y0, va, d_rgba, d_d, d_conf));
+        t.e_wta = t.et.mark();
+        if (ctx->keep_volume) {
+            if ((st = ensure(ctx, ctx->vol_ref, sizeof(float) * (size_t)W * (y1 - y0) * D))) return st;
+            CUL(launch_volume_to_ref_v2(s, tl, y0, y1, va, (float*)ctx->vol_ref.p));
+            fin = (const float*)ctx->vol_ref.p;
+        }
+    } else if (tiled) {
         float *va = (float*)ctx->vol[0].p, *vb = (float*)ctx->vol[1].p;
         float *den_v = (float*)ctx->den_v.p, *den_h = (float*)ctx->den_h.p;
         cudaStream_t s = ctx->stream;
@@ -310,7 +348,7 @@ int asw_create(asw_ctx** out, int device) {
         return ASW_ERR_CUDA;
     }
     for (auto& ev : ctx->ev) cudaEventCreate(&ev);
-    if (tiled_configure() != cudaSuccess) { cudaGetLastError(); asw_destroy(ctx); return ASW_ERR_CUDA; }
+    if (tiled_configure() != cudaSuccess || tma_configure() != cudaSuccess) { cudaGetLastError(); asw_destroy(ctx); return ASW_ERR_CUDA; }
     *out = ctx;
     return ASW_OK;
 }

@@ -167,6 +167,8 @@ def test_fused_vs_reference_golden_png(ctx, oracle, ds):
 EDGE = [  # (W, H, D, iterations)
     (1, 1, 1, 1), (1, 40, 4, 2), (40, 1, 4, 2), (5, 7, 3, 7), (33, 33, 33, 2), (63, 20, 32, 1), (65, 18, 61, 1),
     (130, 17, 100, 1), (70, 35, 256, 1), (129, 9, 200, 2), (64, 64, 16, 0), (50, 20, 61, 3),
+    # Dp multiple of 128: the TMA-pipelined kernels (ragged widths / heights, tiny frames)
+    (20, 12, 128, 2), (200, 30, 256, 2), (97, 41, 120, 3), (1, 9, 128, 1), (31, 8, 255, 1), (65, 7, 128, 7),
 ]
 
 
@@ -220,10 +222,11 @@ def test_known_answers(ctx):
 # ---------------------------------------------------------------------------------------------
 # row bands (the multi-GPU sharding unit) and host-buffer entry point
 
-def test_band_equals_full_frame(ctx):
+@pytest.mark.parametrize("D", [61, 128])
+def test_band_equals_full_frame(ctx, D):
     L, R = load_pair("teddy")
     H = L.shape[0]
-    p = P(ndisp=61, iterations=3)
+    p = P(ndisp=D, iterations=3)
     full = run_fused(ctx, L, R, p)
     for (y0, y1) in [(0, 50), (50, 51), (100, 260), (300, H), (H - 1, H)]:
         b = run_fused(ctx, L, R, p, band=(y0, y1))
