@@ -43,6 +43,7 @@ struct asw_ctx {
     Scratch vol[3];                        // cost volumes (raw / ping / pong)
     Scratch den_v, den_h;                  // hoisted denominators
     Scratch vol_ref;                       // final volume in the reference layout (keep_volume)
+    Scratch fimg_l, fimg_r;                // images as float4 (r, g, b, 0), sampler conversion applied
     enum { kMaxEvents = 64 };
     cudaEvent_t ev[kMaxEvents] = {};
 };
@@ -196,6 +197,7 @@ int run_band(asw_ctx* ctx, const uint8_t* dl, const uint8_t* dr, int W, int H, i
     const size_t tab_bytes = sizeof(float) * b.plane() * (size_t)T;
     int st;
     if (tma) {
+        if ((st = ensure(ctx, ctx->fimg_l, sizeof(float) * 4 * (size_t)W * H)) || (st = ensure(ctx, ctx->fimg_r, sizeof(float) * 4 * (size_t)W * H))) return st;
         if ((st = ensure(ctx, ctx->vL, sizeof(float) * tl.wvl_elems())) || (st = ensure(ctx, ctx->vR, sizeof(float) * tl.wvr_elems())) ||
             (st = ensure(ctx, ctx->hL, sizeof(float) * tl.whl_elems())) || (st = ensure(ctx, ctx->hR, sizeof(float) * tl.whr_elems())))
             return st;
@@ -217,12 +219,15 @@ int run_band(asw_ctx* ctx, const uint8_t* dl, const uint8_t* dr, int W, int H, i
         float *va = (float*)ctx->vol[0].p, *vb = (float*)ctx->vol[1].p;
         float *den_v = (float*)ctx->den_v.p, *den_h = (float*)ctx->den_h.p;
         cudaStream_t s = ctx->stream;
-        CUL(launch_raw_v2(s, dl, dr, tl, ya, yb, p->trunc, va));
+        const float4 *fl = (const float4*)ctx->fimg_l.p, *fr = (const float4*)ctx->fimg_r.p;
+        CUL(launch_unpack_v2(s, dl, W * H, (float4*)ctx->fimg_l.p));
+        CUL(launch_unpack_v2(s, dr, W * H, (float4*)ctx->fimg_r.p));
+        CUL(launch_raw_v2(s, fl, fr, tl, ya, yb, p->trunc, va));
         t.e_raw = t.et.mark();
-        CUL(launch_support_v2(s, true, false, dl, tl, ya, yb, p->gamma_c, p->gamma_p, vL));
-        CUL(launch_support_v2(s, false, false, dl, tl, ya, yb, p->gamma_c, p->gamma_p, hL));
-        CUL(launch_support_v2(s, true, true, dr, tl, ya, yb, p->gamma_c, p->gamma_p, vR));
-        CUL(launch_support_v2(s, false, true, dr, tl, ya, yb, p->gamma_c, p->gamma_p, hR));
+        CUL(launch_support_v2(s, true, false, fl, tl, ya, yb, p->gamma_c, p->gamma_p, vL));
+        CUL(launch_support_v2(s, false, false, fl, tl, ya, yb, p->gamma_c, p->gamma_p, hL));
+        CUL(launch_support_v2(s, true, true, fr, tl, ya, yb, p->gamma_c, p->gamma_p, vR));
+        CUL(launch_support_v2(s, false, true, fr, tl, ya, yb, p->gamma_c, p->gamma_p, hR));
         t.e_supp = t.et.mark();
         for (int it = 0; it < r; it++) {
             const int ylo = max(ya, y0 - (r - 1 - it) * R), yhi = min(yb, y1 + (r - 1 - it) * R);
@@ -358,7 +363,7 @@ int asw_destroy(asw_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     Scratch* all[] = {&ctx->img_l, &ctx->img_r, &ctx->out_rgba, &ctx->out_d, &ctx->out_conf, &ctx->vL, &ctx->hL, &ctx->vR,
-                      &ctx->hR, &ctx->vol[0], &ctx->vol[1], &ctx->vol[2], &ctx->den_v, &ctx->den_h, &ctx->vol_ref};
+                      &ctx->hR, &ctx->vol[0], &ctx->vol[1], &ctx->vol[2], &ctx->den_v, &ctx->den_h, &ctx->vol_ref, &ctx->fimg_l, &ctx->fimg_r};
     for (Scratch* s : all) if (s->p) cudaFree(s->p);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->stream);
