@@ -1,0 +1,105 @@
+"""Multi-process host logic of the sharded paths, on CPU over gloo (world_size 2 and 3).
+
+The compute callback is the CPU oracle run on the rows that can influence the band (r*R halo rows,
+clipped at the frame border) -- the same halo rule asw_disparity_band_device implements on the GPU --
+so the test checks the band geometry, the padding of uneven bands and the all-gather, and that the
+sharded result is bit-identical to the unsharded one."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+from conftest import crop_pair
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _oracle_band(left, right, y0, y1, D=24, r=2):
+    from oracle import asw_oracle as O
+    from stereo_matchin_b200.sharding import band_input_rows
+    H = left.shape[0]
+    ya, yb = band_input_rows(y0, y1, H, 16, r)
+    res = O.asw_hot_path(np.ascontiguousarray(left[ya:yb]), np.ascontiguousarray(right[ya:yb]),
+                         O.OracleParams(ndisp=D, iterations=r), use_fma=True)
+    return res["d_ref"][y0 - ya:y1 - ya].astype(np.uint8)
+
+
+def _worker(rank, world, port, mode, q):
+    import torch.distributed as dist
+    from oracle import asw_oracle as O
+    from stereo_matchin_b200 import sharding
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    O.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        if mode == "bands":
+            L, R = crop_pair("teddy", 40, 0, 120, 151)      # 151 rows: uneven bands
+            full = sharding.disparity_row_sharded(L, R, rank, world, _oracle_band)
+            q.put((rank, full.numpy()))
+        else:
+            pairs = [crop_pair("cones", 30 * i, 20 * i, 64, 40) for i in range(2 * world)]
+            maps = sharding.disparity_pair_sharded(pairs, rank, world, lambda l, r: _oracle_band(l, r, 0, l.shape[0]))
+            q.put((rank, maps.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(world, mode):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, mode, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = {}
+    try:
+        for _ in range(world):
+            rank, arr = q.get(timeout=90)
+            out[rank] = arr
+    finally:
+        for p in procs:
+            p.join(30)
+            if p.is_alive():
+                p.kill()
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    return out
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_row_band_sharding_matches_single_process(world):
+    out = _run(world, "bands")
+    L, R = crop_pair("teddy", 40, 0, 120, 151)
+    ref = _oracle_band(L, R, 0, L.shape[0])
+    for r in range(world):
+        assert np.array_equal(out[r], ref), f"rank {r}: gathered map differs from the unsharded result"
+
+
+def test_pair_sharding_gathers_every_map():
+    world = 2
+    out = _run(world, "pairs")
+    pairs = [crop_pair("cones", 30 * i, 20 * i, 64, 40) for i in range(2 * world)]
+    ref = np.stack([_oracle_band(l, r, 0, l.shape[0]) for l, r in pairs])
+    for r in range(world):
+        assert np.array_equal(out[r], ref)
+
+
+def test_band_geometry():
+    from stereo_matchin_b200 import sharding as s
+    assert s.row_bands(2160, 8) == [(270 * i, 270 * (i + 1)) for i in range(8)]
+    assert s.row_bands(10, 4) == [(0, 2), (2, 5), (5, 7), (7, 10)]
+    assert s.band_input_rows(270, 540, 2160, 16, 7) == (158, 652)          # 112 halo rows per side
+    assert s.band_input_rows(0, 270, 2160, 16, 7) == (0, 382)              # clipped at the frame border
+    rows = s.iteration_rows(270, 540, 2160, 16, 7)
+    assert rows[0] == (174, 636) and rows[-1] == (270, 540)                # halo shrinks by R per iteration
+    assert [b - a for a, b in rows] == [462 - 32 * i for i in range(7)]
+    # halo overhead of the 4K frame: +36 % at 8 GPUs, +4 % at 2
+    assert abs(s.band_work_fraction(2160, 8) - 1.311) < 0.01
+    assert abs(s.band_work_fraction(2160, 2) - 1.044) < 0.01
+    assert s.band_work_fraction(2160, 1) == 1.0
+    assert [len(r) for r in s.pair_shards(1024, 8)] == [128] * 8
