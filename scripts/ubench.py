@@ -12,4 +12,8 @@ for mode in range(4):
         ms = C.c_double()
         v = ub.asw_ubench_lds(mode, f, C.byref(ms))
         rep["lds128"][f"{names[mode]}_fma{f}"] = {"lds_per_ns_per_sm": v, "ms": ms.value}
+ub.asw_ubench_mix.restype = C.c_double
+ub.asw_ubench_mix.argtypes = [C.c_int, C.c_double]
+rep["mix_lane_ops_per_clk_per_sm_at_1965MHz"] = {n: ub.asw_ubench_mix(m, 1965.0) for m, n in
+    enumerate(["fmul+ffma_scalar_tapops(peak 64)", "fmul2+ffma2_packed_tapops(peak 64)", "fmul_only(peak 128)", "ffma_3src_only(peak 128)"])}
 print(json.dumps(rep, indent=1))

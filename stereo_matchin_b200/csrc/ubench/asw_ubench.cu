@@ -84,6 +84,45 @@ __global__ void k_lds_mix(float* out, int iters, int mode) {
     if (s == 123.456f) out[0] = s;
 }
 
+// tap-loop shaped mixes: w = a*b (FMUL); acc = fma(w, c, acc), operands in distinct registers.
+//   mode 0: scalar FMUL + FFMA     mode 1: packed FMUL2 + FFMA2     mode 2: FMUL only     mode 3: FFMA only (3 distinct sources)
+template <int MODE>
+__global__ void k_mix(float* out, int iters, const float* __restrict__ in) {
+    float a[8], b[8], c[8], acc[16];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { a[i] = in[i] + threadIdx.x; b[i] = in[8 + i]; c[i] = in[16 + i]; }
+#pragma unroll
+    for (int i = 0; i < 16; i++) acc[i] = i;
+    for (int it = 0; it < iters; it++) {
+        if (MODE == 0) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) { float w = __fmul_rn(a[i & 7], b[(i * 3) & 7]); acc[i] = __fmaf_rn(w, c[(i * 5) & 7], acc[i]); }
+        } else if (MODE == 1) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                unsigned long long w, aa, bb, cc, ac;
+                asm("mov.b64 %0, {%1, %2};" : "=l"(aa) : "f"(a[i]), "f"(a[(i + 1) & 7]));
+                asm("mov.b64 %0, {%1, %1};" : "=l"(bb) : "f"(b[(i * 3) & 7]));
+                asm("mov.b64 %0, {%1, %2};" : "=l"(cc) : "f"(c[i]), "f"(c[(i + 3) & 7]));
+                asm("mov.b64 %0, {%1, %2};" : "=l"(ac) : "f"(acc[2 * i]), "f"(acc[2 * i + 1]));
+                asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(w) : "l"(aa), "l"(bb));
+                asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(ac) : "l"(w), "l"(cc));
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[2 * i]), "=f"(acc[2 * i + 1]) : "l"(ac));
+            }
+        } else if (MODE == 2) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) acc[i] = __fmul_rn(acc[i], b[i & 7]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; i++) acc[i] = __fmaf_rn(a[i & 7], c[(i * 5) & 7], acc[i]);
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s += acc[i];
+    if (s == 123.456f) out[0] = s;
+}
+
 float time_ms(void (*launch)(void*), void* arg, int reps) {
     cudaEvent_t a, b;
     cudaEventCreate(&a);
@@ -149,4 +188,31 @@ UB_API double asw_ubench_lds(int mode, int fma_per_lds, double* out_ms) {
     if (out_ms) *out_ms = ms;
     double lds = (double)a.blocks * (a.threads / 32) * a.iters;  // warp-level LDS.128 instructions
     return lds / (ms * 1e6) / sms;                                // per ns per SM
+}
+
+// FP32 pipe throughput of tap-shaped instruction mixes, in "tap-ops" (one FMUL + one FMA, scalar
+// equivalent) per clock per SM at `clock_mhz`; the roofline is 64 (128 lanes x 1 FMA/clk / 2 per tap).
+UB_API double asw_ubench_mix(int mode, double clock_mhz) {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    static float* in = nullptr;
+    if (!in) { cudaMalloc(&in, 256); cudaMemset(in, 0, 256); }
+    Arg a{nullptr, 4096, sms * 8, 256, 0};
+    cudaMalloc(&a.out, 64);
+    static float* gin; gin = in;
+    float ms = -1.f;
+    switch (mode) {
+        case 0: ms = time_ms([](void* p) { Arg* a = (Arg*)p; k_mix<0><<<a->blocks, a->threads>>>(a->out, a->iters, gin); }, &a, 5); break;
+        case 1: ms = time_ms([](void* p) { Arg* a = (Arg*)p; k_mix<1><<<a->blocks, a->threads>>>(a->out, a->iters, gin); }, &a, 5); break;
+        case 2: ms = time_ms([](void* p) { Arg* a = (Arg*)p; k_mix<2><<<a->blocks, a->threads>>>(a->out, a->iters, gin); }, &a, 5); break;
+        case 3: ms = time_ms([](void* p) { Arg* a = (Arg*)p; k_mix<3><<<a->blocks, a->threads>>>(a->out, a->iters, gin); }, &a, 5); break;
+        default: break;
+    }
+    cudaFree(a.out);
+    if (ms < 0 || cudaGetLastError() != cudaSuccess) return -1.0;
+    // lane-level ops per iteration: mode 0/1: 16 tap-ops; mode 2/3: 16 single instructions (= 8 tap-op equivalents)
+    double lane_ops = (double)a.blocks * a.threads * a.iters * 16.0;
+    double per_clk_sm = lane_ops / (ms * 1e-3) / (clock_mhz * 1e6) / sms;
+    return per_clk_sm;   // lanes-ops per clock per SM: FMA peak = 128 single instr / 64 tap-ops
 }
