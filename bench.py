@@ -201,8 +201,9 @@ def main():
         for (l, rr), o, of in zip(host_in, host_d, host_full_d):
             if band_mode:   # upload, run the band on device pointers, download the band
                 with torch.cuda.stream(stream):
-                    dl, dr = l.cuda(non_blocking=True), rr.cuda(non_blocking=True)
-                    ctx.disparity_raw(dl.data_ptr(), dr.data_ptr(), W, H, params, None, dev_d[0].data_ptr(), None, band=band)
+                    dev_in[0][0].copy_(l, non_blocking=True)
+                    dev_in[0][1].copy_(rr, non_blocking=True)
+                    ctx.disparity_raw(dev_in[0][0].data_ptr(), dev_in[0][1].data_ptr(), W, H, params, None, dev_d[0].data_ptr(), None, band=band)
                     o.copy_(dev_d[0], non_blocking=True)
                 stream.synchronize()
             else:           # the user-facing call: host buffers in, host buffers out, synchronous
@@ -275,7 +276,7 @@ def main():
         hbm_peak = json.load(open(peaks_file)).get("hbm_gbs") if os.path.exists(peaks_file) else 6650.0
         Dp = (D + 31) // 32 * 32
         pass_bytes = 3.0 * 4 * W * rows_mean * Dp      # tiled kernels: read cost + read denominator + write cost
-        roofline = {"bound": "fp32", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+        roofline = {"bound": "fp32", "kernel": dom.replace("k_vagg_t", "k_vagg_v2 + fix-up/pad launches").replace("k_hagg_t", "k_hagg_v2"), "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "traffic": None, "peak_source": peak_src, "measured_ffma_microbench": ffma,
                     "whole_path_frac": alg_flops(W, rows_mean, D, r) / (tm["total_ms"] * 1e-3) / 1e12 / peak,
                     "v_pass_ms": v_ms, "h_pass_ms": h_ms,
@@ -307,6 +308,10 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    # tensors allocated under the library's stream must be released before that stream is destroyed
+    del dev_in, dev_d, gather, gather_band, host_in, host_d, host_full_d
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
     ctx.close()
 
 
