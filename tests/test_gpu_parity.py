@@ -268,6 +268,20 @@ def test_error_behaviour(ctx):
 # ---------------------------------------------------------------------------------------------
 # BASELINE.json full size (cfg3: 1800 x 1500, 256 disparities) through size-independent properties
 
+def test_full_size_cfg3_is_deterministic(ctx):
+    """Two runs of the whole path on the full-size frame agree bit for bit (catches races in the
+    asynchronous TMA / mbarrier pipelines that small frames do not exercise)."""
+    from stereo_matchin_b200.synth import make_config
+    L, R, _, D = make_config("cfg3_1800x1500_d256")
+    p = P(ndisp=D, iterations=3)
+    a = run_fused(ctx, L, R, p, keep=True)
+    b = run_fused(ctx, L, R, p, keep=True)
+    assert_bit_equal(a["cost"], b["cost"], "cfg3 final volume, run 1 vs run 2")
+    assert_bit_equal(a["conf"], b["conf"], "cfg3 confidence, run 1 vs run 2")
+    c = run_fused(ctx, L, R, p, family=1, band=(1000, 1016), keep=True)      # generic kernels on a band
+    assert_bit_equal(a["cost"][:, 1000:1016], c["cost"], "cfg3 final volume vs generic CUDA kernels")
+
+
 def test_full_size_cfg3_properties(ctx, oracle):
     from stereo_matchin_b200.synth import make_config
     L, R, _, D = make_config("cfg3_1800x1500_d256")
