@@ -169,6 +169,7 @@ EDGE = [  # (W, H, D, iterations)
     (130, 17, 100, 1), (70, 35, 256, 1), (129, 9, 200, 2), (64, 64, 16, 0), (50, 20, 61, 3),
     # Dp multiple of 128: the TMA-pipelined kernels (ragged widths / heights, tiny frames)
     (20, 12, 128, 2), (200, 30, 256, 2), (97, 41, 120, 3), (1, 9, 128, 1), (31, 8, 255, 1), (65, 7, 128, 7),
+    (40, 10, 384, 1), (70, 9, 500, 2),
 ]
 
 
