@@ -158,6 +158,38 @@ ASW_API int asw_WTA(asw_ctx* ctx, int W, int H, const asw_params* prm, const flo
                     float* d_est_reference, float* d_est_target, uint8_t* d_output_target_rgba,
                     float* d_confidence_reference, float* d_confidence_target);
 
+/* ---- consumers of the hot path ("next" rows): consistency, refinement, penalised WTA, median ----
+ * Device pointers, reference layouts; argument order mirrors the clSetKernelArg sequences. */
+
+/* kernels/consist.cl:3-34 `Constistency(ref, tar, confidence_ref, confidence_tar, output, output_red)`;
+ * args main.cpp:531-536.  Disparity images are read as v/255*(ndisp-1); output / output_red may be NULL. */
+ASW_API int asw_Constistency(asw_ctx* ctx, int W, int H, const asw_params* prm, const uint8_t* d_ref_rgba,
+                             const uint8_t* d_tar_rgba, float* d_confidence_ref, float* d_confidence_tar,
+                             uint8_t* d_output_rgba, uint8_t* d_output_red_rgba);
+/* kernels/asw_refinement_v.cl:13-51 `asw_ref_v(input, input_est, confidence, output_REF)`; args main.cpp:547-551.
+ * output_REF holds two W*H planes (value, denominator). */
+ASW_API int asw_ref_v(asw_ctx* ctx, int W, int H, const asw_params* prm, const uint8_t* d_input_rgba,
+                      const uint8_t* d_input_est_rgba, const float* d_confidence, float* d_output_REF);
+/* kernels/asw_refinement_h.cl:16-53 `asw_ref_h(input, confidence, input_REF, output_REF)`; args main.cpp:563-567 */
+ASW_API int asw_ref_h(asw_ctx* ctx, int W, int H, const asw_params* prm, const uint8_t* d_input_rgba, const float* d_confidence,
+                      const float* d_input_REF, float* d_output_REF);
+/* kernels/asw_wta_ref.cl:2-68 `asw_WTA_REF(agg_d, ref, ref_target, output, output_target, disp_ref,
+ * disp_ref_target, confidence, confidence_target)`; args main.cpp:580-588.  As in the reference, the
+ * target confidence overwrites `confidence` and confidence_target is left untouched (:63,66). */
+ASW_API int asw_WTA_REF(asw_ctx* ctx, int W, int H, const asw_params* prm, const float* d_agg_d, const float* d_ref,
+                        const float* d_ref_target, uint8_t* d_output_rgba, uint8_t* d_output_target_rgba, float* d_disp_ref,
+                        float* d_disp_ref_target, float* d_confidence, float* d_confidence_target);
+/* kernels/median.cl:58-88 `Median(input, output)`; args main.cpp:617-618 */
+ASW_API int asw_Median(asw_ctx* ctx, int W, int H, const uint8_t* d_input_rgba, uint8_t* d_output_rgba);
+
+/* The whole ASW method of main.cpp:463-631 on host buffers: hot path (fused kernels), consistency,
+ * `refine_iters` (reference: k = 6, main.cpp:176) refinement rounds, median.  Outputs (any may be
+ * NULL), each W*H*4: the final disparity image (the reference's asw_disparity.png) and the two
+ * consistency images (asw_consistency_pre-reff.png / asw_consistency_post-reff.png). */
+ASW_API int asw_stereo(asw_ctx* ctx, const uint8_t* left_rgba, const uint8_t* right_rgba, int W, int H, const asw_params* prm,
+                       int refine_iters, uint8_t* disparity_rgba, uint8_t* consistency_pre_rgba, uint8_t* consistency_post_rgba,
+                       asw_timing* timing);
+
 /* ---- device memory helpers (so a plain C/C++ host needs no CUDA headers) -------------
  * Replace clCreateBuffer / clCreateImage2D(COPY_HOST_PTR) / clEnqueueReadImage /
  * clReleaseMemObject, main.cpp:243-256,434-457,621-629,712-738. */

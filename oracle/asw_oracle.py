@@ -63,6 +63,12 @@ def lib() -> C.CDLL:
         _lib.oracle_asw_hcost_aggregation.argtypes = [f32p, f32p, f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f32p]
         _lib.oracle_asw_wta.argtypes = [f32p, C.c_int, C.c_int, C.c_int, u8p, f32p, f32p, u8p, f32p, f32p]
         _lib.oracle_consistency.argtypes = [u8p, u8p, C.c_int, C.c_int, C.c_float, f32p, f32p, u8p, u8p]
+        _lib.oracle_asw_ref_v.argtypes = [u8p, u8p, f32p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, f32p]
+        _lib.oracle_asw_ref_h.argtypes = [u8p, f32p, f32p, C.c_int, C.c_int, C.c_int, C.c_int, f32p]
+        _lib.oracle_asw_wta_ref.argtypes = [f32p, f32p, f32p, C.c_int, C.c_int, C.c_int, C.c_int, u8p, u8p, f32p, f32p, f32p]
+        _lib.oracle_median.argtypes = [u8p, C.c_int, C.c_int, u8p]
+        _lib.oracle_asw_full.restype = C.c_int
+        _lib.oracle_asw_full.argtypes = [u8p, u8p, C.c_int, C.c_int, C.POINTER(_Params), C.c_int, C.c_int, u8p, u8p, u8p]
         _lib.oracle_asw_hot_path.restype = C.c_int
         _lib.oracle_asw_hot_path.argtypes = [u8p, u8p, C.c_int, C.c_int, C.POINTER(_Params), C.c_int,
                                              f32p, u8p, u8p, f32p, f32p, f32p, f32p]
@@ -171,4 +177,56 @@ def asw_hot_path(left: np.ndarray, right: np.ndarray, params: OracleParams | Non
                                    _f32(r["conf_ref"]), _f32(r.get("conf_tar")))
     if rc != 0:
         raise RuntimeError(f"oracle_asw_hot_path failed rc={rc}")
+    return r
+
+
+# ---- consumers of the hot path (asw_tail_oracle.c) -------------------------------------------------
+
+def asw_ref_v(img, est_rgba, conf, radius: int = 16, dscale: float = 60.0, use_fma: bool = False) -> np.ndarray:
+    img, est_rgba = _img(img), _img(est_rgba)
+    H, W, _ = img.shape
+    conf = np.ascontiguousarray(conf, np.float32)
+    out = np.empty((2, H, W), np.float32)
+    lib().oracle_asw_ref_v(_u8(img), _u8(est_rgba), _f32(conf), W, H, radius, dscale, int(use_fma), _f32(out))
+    return out
+
+
+def asw_ref_h(img, conf, vref, radius: int = 16, use_fma: bool = False) -> np.ndarray:
+    img = _img(img)
+    H, W, _ = img.shape
+    conf, vref = np.ascontiguousarray(conf, np.float32), np.ascontiguousarray(vref, np.float32)
+    out = np.empty((2, H, W), np.float32)
+    lib().oracle_asw_ref_h(_u8(img), _f32(conf), _f32(vref), W, H, radius, int(use_fma), _f32(out))
+    return out
+
+
+def asw_wta_ref(cost, href_l, href_r, use_fma: bool = False) -> dict:
+    cost = np.ascontiguousarray(cost, np.float32)
+    D, H, W = cost.shape
+    r = {"left": np.empty((H, W, 4), np.uint8), "right": np.empty((H, W, 4), np.uint8), "d_ref": np.empty((H, W), np.float32),
+         "d_tar": np.empty((H, W), np.float32), "confidence": np.empty((H, W), np.float32)}
+    lib().oracle_asw_wta_ref(_f32(cost), _f32(np.ascontiguousarray(href_l, np.float32)), _f32(np.ascontiguousarray(href_r, np.float32)),
+                             W, H, D, int(use_fma), _u8(r["left"]), _u8(r["right"]), _f32(r["d_ref"]), _f32(r["d_tar"]), _f32(r["confidence"]))
+    return r
+
+
+def median(img_rgba) -> np.ndarray:
+    img_rgba = _img(img_rgba)
+    H, W, _ = img_rgba.shape
+    out = np.empty_like(img_rgba)
+    lib().oracle_median(_u8(img_rgba), W, H, _u8(out))
+    return out
+
+
+def asw_full(left, right, params: OracleParams | None = None, use_fma: bool = False, refine_iters: int = 6) -> dict:
+    """The whole ASW method of main.cpp:463-631: hot path, consistency, k refinement rounds, median."""
+    params = params or OracleParams()
+    left, right = _img(left), _img(right)
+    H, W, _ = left.shape
+    r = {"disparity": np.empty((H, W, 4), np.uint8), "pre_red": np.empty((H, W, 4), np.uint8), "post_red": np.empty((H, W, 4), np.uint8)}
+    p = params.c()
+    rc = lib().oracle_asw_full(_u8(left), _u8(right), W, H, C.byref(p), int(use_fma), refine_iters, _u8(r["disparity"]),
+                               _u8(r["pre_red"]), _u8(r["post_red"]))
+    if rc != 0:
+        raise RuntimeError(f"oracle_asw_full failed rc={rc}")
     return r

@@ -26,7 +26,8 @@ EXPORTS = [
     "asw_version", "asw_strerror", "asw_create", "asw_destroy", "asw_last_error", "asw_stream", "asw_sync",
     "asw_device_info", "asw_params_default", "asw_disparity", "asw_disparity_device", "asw_disparity_band_device",
     "asw_set_keep_volume", "asw_final_volume", "asw_Aggr", "asw_vSupport", "asw_hSupport", "asw_vCostAggregation",
-    "asw_hCostAggregation", "asw_WTA", "asw_dev_alloc", "asw_dev_free", "asw_memcpy_h2d", "asw_memcpy_d2h",
+    "asw_hCostAggregation", "asw_WTA", "asw_Constistency", "asw_ref_v", "asw_ref_h", "asw_WTA_REF", "asw_Median", "asw_stereo",
+    "asw_dev_alloc", "asw_dev_free", "asw_memcpy_h2d", "asw_memcpy_d2h",
     "asw_host_alloc", "asw_host_free", "asw_set_kernel_family",
 ]
 
@@ -103,6 +104,12 @@ def load_library() -> C.CDLL:
     lib.asw_vCostAggregation.argtypes = [vp, C.c_int, C.c_int, pp, f32p, f32p, f32p, f32p, f32p]
     lib.asw_hCostAggregation.argtypes = [vp, C.c_int, C.c_int, pp, f32p, f32p, f32p, f32p, f32p]
     lib.asw_WTA.argtypes = [vp, C.c_int, C.c_int, pp, f32p, u8p, f32p, f32p, u8p, f32p, f32p]
+    lib.asw_Constistency.argtypes = [vp, C.c_int, C.c_int, pp, u8p, u8p, f32p, f32p, u8p, u8p]
+    lib.asw_ref_v.argtypes = [vp, C.c_int, C.c_int, pp, u8p, u8p, f32p, f32p]
+    lib.asw_ref_h.argtypes = [vp, C.c_int, C.c_int, pp, u8p, f32p, f32p, f32p]
+    lib.asw_WTA_REF.argtypes = [vp, C.c_int, C.c_int, pp, f32p, f32p, f32p, u8p, u8p, f32p, f32p, f32p, f32p]
+    lib.asw_Median.argtypes = [vp, C.c_int, C.c_int, u8p, u8p]
+    lib.asw_stereo.argtypes = [vp, u8p, u8p, C.c_int, C.c_int, pp, C.c_int, u8p, u8p, u8p, tp]
     lib.asw_dev_alloc.argtypes = [vp, C.POINTER(vp), C.c_size_t]
     lib.asw_dev_free.argtypes = [vp, vp]
     lib.asw_memcpy_h2d.argtypes = [vp, vp, vp, C.c_size_t]
@@ -261,6 +268,40 @@ class AswContext:
             st = self.lib.asw_disparity_device(self.h, left_ptr, right_ptr, W, H, C.byref(p), rgba_ptr, d_ptr, conf_ptr, tref)
         self._check(st)
         return tm.as_dict() if tm is not None else None
+
+    def stereo(self, left: np.ndarray, right: np.ndarray, params: AswParams | None = None, refine_iters: int = 6) -> dict:
+        """The whole ASW method (asw_stereo): final disparity image + the two consistency images."""
+        params = params or AswParams()
+        left, right = _rgba(left), _rgba(right)
+        H, W, _ = left.shape
+        out = {k: np.empty((H, W, 4), np.uint8) for k in ("disparity", "pre_red", "post_red")}
+        tm = CTiming()
+        p = params.c()
+        self._check(self.lib.asw_stereo(self.h, left.ctypes.data, right.ctypes.data, W, H, C.byref(p), refine_iters,
+                                        out["disparity"].ctypes.data, out["pre_red"].ctypes.data, out["post_red"].ctypes.data, C.byref(tm)))
+        out["timing"] = tm.as_dict()
+        return out
+
+    def asw_Constistency(self, W, H, params, ref, tar, confidence_ref, confidence_tar, output, output_red):
+        p = params.c()
+        self._check(self.lib.asw_Constistency(self.h, W, H, C.byref(p), ref, tar, confidence_ref, confidence_tar, output, output_red))
+
+    def asw_ref_v(self, W, H, params, input_, input_est, confidence, output_REF):
+        p = params.c()
+        self._check(self.lib.asw_ref_v(self.h, W, H, C.byref(p), input_, input_est, confidence, output_REF))
+
+    def asw_ref_h(self, W, H, params, input_, confidence, input_REF, output_REF):
+        p = params.c()
+        self._check(self.lib.asw_ref_h(self.h, W, H, C.byref(p), input_, confidence, input_REF, output_REF))
+
+    def asw_WTA_REF(self, W, H, params, agg_d, ref, ref_target, output, output_target, disp_ref, disp_ref_target, confidence,
+                    confidence_target):
+        p = params.c()
+        self._check(self.lib.asw_WTA_REF(self.h, W, H, C.byref(p), agg_d, ref, ref_target, output, output_target, disp_ref,
+                                         disp_ref_target, confidence, confidence_target))
+
+    def asw_Median(self, W, H, input_, output):
+        self._check(self.lib.asw_Median(self.h, W, H, input_, output))
 
     def final_volume_ptr(self) -> int:
         return int(self.lib.asw_final_volume(self.h) or 0)

@@ -15,6 +15,7 @@
 #include "asw_kernels_basic.cuh"
 #include "asw_kernels_tiled.cuh"
 #include "asw_kernels_tma.cuh"
+#include "asw_kernels_tail.cuh"
 
 using namespace asw;
 
@@ -44,6 +45,7 @@ struct asw_ctx {
     Scratch den_v, den_h;                  // hoisted denominators
     Scratch vol_ref;                       // final volume in the reference layout (keep_volume)
     Scratch fimg_l, fimg_r;                // images as float4 (r, g, b, 0), sampler conversion applied
+    Scratch tail[12];                      // whole-method buffers (asw_stereo)
     enum { kMaxEvents = 64 };
     cudaEvent_t ev[kMaxEvents] = {};
 };
@@ -365,6 +367,7 @@ int asw_destroy(asw_ctx* ctx) {
     Scratch* all[] = {&ctx->img_l, &ctx->img_r, &ctx->out_rgba, &ctx->out_d, &ctx->out_conf, &ctx->vL, &ctx->hL, &ctx->vR,
                       &ctx->hR, &ctx->vol[0], &ctx->vol[1], &ctx->vol[2], &ctx->den_v, &ctx->den_h, &ctx->vol_ref, &ctx->fimg_l, &ctx->fimg_r};
     for (Scratch* s : all) if (s->p) cudaFree(s->p);
+    for (Scratch& s : ctx->tail) if (s.p) cudaFree(s.p);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -495,6 +498,109 @@ int asw_WTA(asw_ctx* ctx, int W, int H, const asw_params* prm, const float* cost
             float* d_tar, uint8_t* out_tar_rgba, float* conf_ref, float* conf_tar) {
     OP_PROLOGUE(cost)
     return launch_wta(ctx, b, 0, H, 0, prm, cost, out_rgba, nullptr, d_ref, d_tar, out_tar_rgba, conf_ref, conf_tar);
+}
+
+// ---- consumers of the hot path -----------------------------------------------------------------
+int asw_Constistency(asw_ctx* ctx, int W, int H, const asw_params* prm, const uint8_t* ref, const uint8_t* tar, float* conf_ref,
+                     float* conf_tar, uint8_t* out, uint8_t* out_red) {
+    OP_PROLOGUE(ref && tar)
+    (void)b;
+    const int n = W * H;
+    k_consistency<<<(n + 255) / 256, 256, 0, ctx->stream>>>((const uint32_t*)ref, (const uint32_t*)tar, n, (float)(prm->ndisp - 1), conf_ref,
+                                                          conf_tar, (uint32_t*)out, (uint32_t*)out_red);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return ASW_OK;
+}
+
+int asw_ref_v(asw_ctx* ctx, int W, int H, const asw_params* prm, const uint8_t* img, const uint8_t* est, const float* conf, float* out) {
+    OP_PROLOGUE(img && est && conf && out)
+    (void)b;
+    k_ref_v<<<(unsigned)((W + 127) / 128) * H, 128, 0, ctx->stream>>>((const uint32_t*)img, (const uint32_t*)est, conf, W, H, prm->radius,
+                                                             (float)(prm->ndisp - 1), out);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return ASW_OK;
+}
+
+int asw_ref_h(asw_ctx* ctx, int W, int H, const asw_params* prm, const uint8_t* img, const float* conf, const float* in, float* out) {
+    OP_PROLOGUE(img && conf && in && out)
+    (void)b;
+    k_ref_h<<<(unsigned)((W + 127) / 128) * H, 128, 0, ctx->stream>>>((const uint32_t*)img, conf, in, W, H, prm->radius, out);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return ASW_OK;
+}
+
+int asw_WTA_REF(asw_ctx* ctx, int W, int H, const asw_params* prm, const float* agg, const float* ref, const float* ref_t, uint8_t* out,
+                uint8_t* out_t, float* disp_ref, float* disp_ref_t, float* confidence, float* confidence_target) {
+    (void)confidence_target;   // never written, as in asw_wta_ref.cl:63,66
+    OP_PROLOGUE(agg && ref && ref_t && out && out_t && confidence)
+    (void)b;
+    k_wta_ref<<<(unsigned)((W + 127) / 128) * H, 128, 0, ctx->stream>>>(agg, ref, ref_t, W, H, prm->ndisp, (uint32_t*)out, (uint32_t*)out_t, disp_ref,
+                                                               disp_ref_t, confidence);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return ASW_OK;
+}
+
+int asw_Median(asw_ctx* ctx, int W, int H, const uint8_t* in, uint8_t* out) {
+    if (!ctx) return ASW_ERR_INVALID;
+    if (W <= 0 || H <= 0) return fail(ctx, ASW_ERR_INVALID, "bad image size");
+    if (!in || !out) return fail(ctx, ASW_ERR_INVALID, "device pointer is NULL");
+    CU(cudaSetDevice(ctx->device));
+    k_median<<<(unsigned)((W + 127) / 128) * H, 128, 0, ctx->stream>>>((const uint32_t*)in, W, H, (uint32_t*)out);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return ASW_OK;
+}
+
+// The whole method, main.cpp:463-631: fused hot path -> right-view WTA -> consistency -> k x (ref_v L,R;
+// ref_h L,R; WTA_REF; consistency) -> median.
+int asw_stereo(asw_ctx* ctx, const uint8_t* left, const uint8_t* right, int W, int H, const asw_params* prm, int refine_iters,
+               uint8_t* disparity, uint8_t* pre, uint8_t* post, asw_timing* tm) {
+    int st = check_params(ctx, W, H, prm);
+    if (st) return st;
+    if (!left || !right) return fail(ctx, ASW_ERR_INVALID, "image pointer is NULL");
+    if (refine_iters < 0) return fail(ctx, ASW_ERR_INVALID, "refine_iters must be >= 0");
+    CU(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)W * H;
+    if ((st = ensure(ctx, ctx->img_l, n * 4)) || (st = ensure(ctx, ctx->img_r, n * 4))) return st;
+    // 0 left_wta 1 right_wta 2 conf_ref 3 conf_tar 4 consistency 5 red 6 red_reff 7 vref_l 8 vref_r 9 href_l 10 href_r 11 final
+    const size_t sz[12] = {n * 4, n * 4, n * 4, n * 4, n * 4, n * 4, n * 4, n * 8, n * 8, n * 8, n * 8, n * 4};
+    for (int i = 0; i < 12; i++)
+        if ((st = ensure(ctx, ctx->tail[i], sz[i]))) return st;
+    uint8_t *lw = (uint8_t*)ctx->tail[0].p, *rw = (uint8_t*)ctx->tail[1].p, *ce = (uint8_t*)ctx->tail[4].p, *red = (uint8_t*)ctx->tail[5].p,
+            *red2 = (uint8_t*)ctx->tail[6].p, *fin = (uint8_t*)ctx->tail[11].p;
+    float *cr = (float*)ctx->tail[2].p, *ct = (float*)ctx->tail[3].p, *vl = (float*)ctx->tail[7].p, *vr = (float*)ctx->tail[8].p,
+          *hl = (float*)ctx->tail[9].p, *hr = (float*)ctx->tail[10].p;
+    const uint8_t *dl = (const uint8_t*)ctx->img_l.p, *dr = (const uint8_t*)ctx->img_r.p;
+    CU(cudaMemcpyAsync(ctx->img_l.p, left, n * 4, cudaMemcpyHostToDevice, ctx->stream));      // main.cpp:243
+    CU(cudaMemcpyAsync(ctx->img_r.p, right, n * 4, cudaMemcpyHostToDevice, ctx->stream));     // main.cpp:244
+    const int keep = ctx->keep_volume;
+    ctx->keep_volume = 1;                                          // WTA_REF and the right view read the final volume
+    st = run_band(ctx, dl, dr, W, H, 0, H, prm, nullptr, nullptr, nullptr, tm);
+    ctx->keep_volume = keep;
+    if (st) return st;
+    const float* vol = ctx->final_volume;
+    // left + right view and both confidences (asw_wta.cl, main.cpp:519-526)
+    if ((st = asw_WTA(ctx, W, H, prm, vol, lw, nullptr, nullptr, rw, cr, ct))) return st;
+    if ((st = asw_Constistency(ctx, W, H, prm, lw, rw, cr, ct, ce, red))) return st;          // main.cpp:531-536
+    for (int i = 0; i < refine_iters; i++) {                                                  // main.cpp:545-614
+        if ((st = asw_ref_v(ctx, W, H, prm, dl, ce, cr, vl))) return st;
+        if ((st = asw_ref_v(ctx, W, H, prm, dr, rw, ct, vr))) return st;
+        if ((st = asw_ref_h(ctx, W, H, prm, dl, cr, vl, hl))) return st;
+        if ((st = asw_ref_h(ctx, W, H, prm, dr, ct, vr, hr))) return st;
+        if ((st = asw_WTA_REF(ctx, W, H, prm, vol, hl, hr, lw, rw, nullptr, nullptr, cr, ct))) return st;
+        if ((st = asw_Constistency(ctx, W, H, prm, lw, rw, cr, ct, ce, red2))) return st;
+    }
+    if ((st = asw_Median(ctx, W, H, ce, fin))) return st;                                     // main.cpp:617-619
+    if (disparity) CU(cudaMemcpyAsync(disparity, fin, n * 4, cudaMemcpyDeviceToHost, ctx->stream));                 // main.cpp:621
+    if (pre) CU(cudaMemcpyAsync(pre, red, n * 4, cudaMemcpyDeviceToHost, ctx->stream));                             // main.cpp:625
+    if (post) CU(cudaMemcpyAsync(post, refine_iters ? red2 : red, n * 4, cudaMemcpyDeviceToHost, ctx->stream));     // main.cpp:629
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (tm) tm->kernel_launches = ctx->launches;
+    return ASW_OK;
 }
 
 // ---- memory helpers --------------------------------------------------------------------------
