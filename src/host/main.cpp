@@ -8,10 +8,13 @@
 //   * per-stage timings come from device events (CL profiling there, CUDA events here)
 // What is replaced: the OpenCL platform/device/context/program/queue setup and the enqueue
 // sequence (main.cpp:119-130,158-172,210-256,434-526) -> asw_create + asw_disparity.
-// Out of scope (columns written as 0): the cross-based method and the refinement tail.
+// --method hot (default) runs the hot path only and writes asw_disparity<suffix>.png = the WTA image;
+// --method whole runs the whole ASW method (asw_stereo: + consistency, k refinement rounds, median,
+// main.cpp:529-631) and writes the reference's three ASW PNGs (main.cpp:621-631) with the suffix.
+// Out of scope (columns written as 0): the cross-based method; per-stage times of the refinement tail.
 //
 // Usage: stereo_matching [--pics pics.txt] [--root DIR] [--runs 10] [--device 0] [--ndisp 61]
-//                        [--iterations 7] [--out-suffix _wta] [--log FILE]
+//                        [--iterations 7] [--method hot|whole] [--refine 6] [--out-suffix _wta] [--log FILE]
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -36,7 +39,8 @@ static const char* kHeader =
 
 int main(int argc, char** argv) {
     std::string pics = "pics.txt", root = ".", suffix = "_wta", log_name;
-    int runs = 10, device = 0;
+    int runs = 10, device = 0, refine = 6;   // k = 6, main.cpp:176
+    bool whole = false;
     asw_params prm;
     asw_params_default(&prm);
     for (int i = 1; i < argc; i++) {
@@ -51,6 +55,12 @@ int main(int argc, char** argv) {
         else if (a == "--device") device = atoi(next("--device"));
         else if (a == "--ndisp") prm.ndisp = atoi(next("--ndisp"));
         else if (a == "--iterations") prm.iterations = atoi(next("--iterations"));
+        else if (a == "--refine") refine = atoi(next("--refine"));
+        else if (a == "--method") {
+            std::string m = next("--method");
+            if (m != "hot" && m != "whole") { fprintf(stderr, "--method must be hot or whole\n"); return 2; }
+            whole = m == "whole";
+        }
         else if (a == "--out-suffix") suffix = next("--out-suffix");
         else if (a == "--log") log_name = next("--log");
         else { fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
@@ -97,22 +107,33 @@ int main(int argc, char** argv) {
             continue;
         }
         const unsigned W = imgL.width, H = imgL.height;
-        std::vector<unsigned char> disp((size_t)W * H * 4);
+        std::vector<unsigned char> disp((size_t)W * H * 4), pre, post;
+        if (whole) { pre.resize(disp.size()); post.resize(disp.size()); }
         double sum_total = 0;
         for (int run = 0; run < runs; run++) {
             fprintf(to_file, "\nRun %d \t", run + 1);
             printf("\n---Working...\nRaw cost aggregation..  \ngestalt principle - support area.. \nCost aggregation.. \nWTA.. ");
             asw_timing t;
-            st = asw_disparity(ctx, imgL.pixel.data(), imgR.pixel.data(), (int)W, (int)H, &prm, disp.data(), nullptr, nullptr, &t);
+            if (whole)
+                st = asw_stereo(ctx, imgL.pixel.data(), imgR.pixel.data(), (int)W, (int)H, &prm, refine, disp.data(), pre.data(), post.data(), &t);
+            else
+                st = asw_disparity(ctx, imgL.pixel.data(), imgR.pixel.data(), (int)W, (int)H, &prm, disp.data(), nullptr, nullptr, &t);
             if (st != ASW_OK) {
                 printf("ASW error executing hot path: %d (%s)\n", st, asw_last_error(ctx));   // ErCheck prints and continues
                 rc = 1;
                 continue;
             }
             if (run == 0) {   // the reference's PNGs on disk come from run 1
-                std::string out = root + "/" + folder_name[img] + "/asw_disparity" + suffix + ".png";
-                unsigned e = png_io::encode(out, disp, W, H);
-                if (e) { fprintf(stderr, "cannot write %s: %s\n", out.c_str(), png_io::error_text(e)); rc = 1; }
+                const std::string dir = root + "/" + folder_name[img] + "/";
+                auto save = [&](const std::string& name, const std::vector<unsigned char>& px) {
+                    unsigned e = png_io::encode(dir + name + suffix + ".png", px, W, H);
+                    if (e) { fprintf(stderr, "cannot write %s: %s\n", (dir + name + suffix + ".png").c_str(), png_io::error_text(e)); rc = 1; }
+                };
+                save("asw_disparity", disp);                                    // main.cpp:621-623
+                if (whole) {
+                    save("asw_consistency_pre-reff", pre);                      // main.cpp:625-627
+                    save("asw_consistency_post-reff", post);                    // main.cpp:629-631
+                }
             }
             for (int c = 0; c < 14; c++) fprintf(to_file, "%0.3f\t", 0.0);   // cross-based columns: out of scope
             fprintf(to_file, "\t\t");

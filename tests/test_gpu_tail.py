@@ -121,3 +121,23 @@ def test_whole_method_vs_reference_disparity_png(ctx, ds):
     assert pct <= (0.0 if ds == "tsukuba" else 0.01), f"{ds}: asw_disparity.png differs on {pct:.4f} % of the pixels"
     gp = load_rgba(os.path.join(GOLDEN, ds, "asw_consistency_post-reff.png"))
     assert 100.0 * float((gp != got["post_red"]).any(-1).mean()) <= (0.0 if ds == "tsukuba" else 0.01)
+
+
+def test_host_binary_whole_method(tmp_path):
+    """The pics.txt-driven host program (src/host, C++ on the C ABI) reproduces the reference's PNGs."""
+    import shutil
+    import subprocess
+    from conftest import PAIRS
+    exe = os.path.join(os.path.dirname(GOLDEN), "..", "src", "host", "stereo_matching")
+    assert os.path.exists(exe), "run `python -m stereo_matchin_b200.build` first"
+    os.makedirs(tmp_path / "tsukuba")
+    for f in PAIRS["tsukuba"]:
+        shutil.copy(os.path.join(GOLDEN, "tsukuba", f), tmp_path / "tsukuba" / f)
+    (tmp_path / "pics.txt").write_text("tsukuba/im1.png\ntsukuba/im5.png\n")
+    r = subprocess.run([exe, "--pics", str(tmp_path / "pics.txt"), "--root", str(tmp_path), "--runs", "2", "--method", "whole",
+                        "--out-suffix", "", "--log", str(tmp_path / "log.tsv")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    for name in ("asw_disparity.png", "asw_consistency_pre-reff.png", "asw_consistency_post-reff.png"):
+        assert np.array_equal(load_rgba(str(tmp_path / "tsukuba" / name)), load_rgba(os.path.join(GOLDEN, "tsukuba", name))), name
+    log = (tmp_path / "log.tsv").read_text()
+    assert "total WTA method" in log and "Run 2" in log
