@@ -16,4 +16,9 @@ ub.asw_ubench_mix.restype = C.c_double
 ub.asw_ubench_mix.argtypes = [C.c_int, C.c_double]
 rep["mix_lane_ops_per_clk_per_sm_at_1965MHz"] = {n: ub.asw_ubench_mix(m, 1965.0) for m, n in
     enumerate(["fmul+ffma_scalar_tapops(peak 64)", "fmul2+ffma2_packed_tapops(peak 64)", "fmul_only(peak 128)", "ffma_3src_only(peak 128)"])}
+ub.asw_ubench_lds_rate.restype = C.c_double
+ub.asw_ubench_lds_rate.argtypes = [C.c_int, C.c_int]
+pat = ["distinct", "broadcast", "l==l+16 (16 distinct)", "pairs (16 distinct)", "l mod 8 (8 distinct)", "groups of 4 (8 distinct)",
+       "groups of 8 (4 distinct)"]
+rep["lds_sm_cycles_per_warp_instruction"] = {f"LDS.{8 * w} {pat[p]}": round(ub.asw_ubench_lds_rate(w, p), 3) for w in (4, 8, 16) for p in range(7)}
 print(json.dumps(rep, indent=1))

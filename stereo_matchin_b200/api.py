@@ -17,7 +17,7 @@ from dataclasses import dataclass
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libasw_b200.so")
+LIB_PATH = os.environ.get("ASW_B200_LIB") or os.path.join(_PKG, "libasw_b200.so")   # override: A/B of experimental builds
 
 ASW_OK, ASW_ERR_INVALID, ASW_ERR_CUDA, ASW_ERR_NOMEM, ASW_ERR_UNSUPPORTED = range(5)
 

@@ -4,6 +4,7 @@
 // and the other probes document the shared-memory / packed-FP32 behaviour the tiled kernels
 // were designed around (profiles/).
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -150,6 +151,103 @@ struct Arg {
 };
 
 }  // namespace
+
+// ---- precise shared-memory issue-rate probe -----------------------------------------------------
+// 16 unrolled loads per iteration at immediate offsets (1 issue slot per load), all warps of the SM
+// active; reports SM cycles per warp-level load instruction measured with clock64 on the SM itself.
+//   width: 4, 8, 16 bytes per lane.  pattern: 0 all lanes distinct & contiguous, 1 full broadcast,
+//   2 lanes l and l+16 share (16 distinct), 3 lane pairs (2k, 2k+1) share (16 distinct),
+//   4 lanes l, l+8, l+16, l+24 share (8 distinct), 5 groups of 4 consecutive lanes share (8 distinct),
+//   6 groups of 8 consecutive lanes share (4 distinct)
+template <int WIDTH>
+__global__ void k_lds_rate(float* out, long long* cycles, int iters, int pattern) {
+    __shared__ __align__(16) float buf[8 * 1024];
+    for (int i = threadIdx.x; i < 8 * 1024; i += blockDim.x) buf[i] = (float)i;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int idx;
+    switch (pattern) {
+        case 0: idx = lane; break;
+        case 1: idx = 0; break;
+        case 2: idx = lane & 15; break;
+        case 3: idx = lane >> 1; break;
+        case 4: idx = lane & 7; break;
+        case 5: idx = lane >> 2; break;
+        default: idx = lane >> 3; break;
+    }
+    const unsigned base0 = (unsigned)__cvta_generic_to_shared(buf) + (unsigned)(idx * WIDTH) + (unsigned)(warp & 3) * 4096u;
+    float s = 0.f;
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) {
+        const unsigned base = base0 + ((unsigned)(it & 1) << 13);   // the address changes every iteration: nothing can be reused
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            if (WIDTH == 16) {
+                float4 v;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(base + u * 512) : "memory");
+                s += v.x;
+            } else if (WIDTH == 8) {
+                float2 v;
+                asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(base + u * 512) : "memory");
+                s += v.x;
+            } else {
+                float v;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(base + u * 512) : "memory");
+                s += v;
+            }
+        }
+    }
+    const long long t1 = clock64();
+    // the CTA's span: earliest start to latest end over its warps (the scheduler favours old warps)
+    __shared__ unsigned long long tmin, tmax;
+    if (threadIdx.x == 0) { tmin = ~0ull; tmax = 0ull; }
+    __syncthreads();
+    if (lane == 0) { atomicMin(&tmin, (unsigned long long)t0); atomicMax(&tmax, (unsigned long long)t1); }
+    __syncthreads();
+    if (threadIdx.x == 0) cycles[blockIdx.x] = (long long)(tmax - tmin);
+    if (s == 123.456f) out[0] = s;
+}
+
+// SM cycles per warp-level LDS instruction (all 32 warps of one 1024-thread CTA per SM issuing)
+UB_API double asw_ubench_lds_rate(int width, int pattern) {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    float* out;
+    long long* cyc;
+    cudaMalloc(&out, 64);
+    cudaMalloc(&cyc, sizeof(long long) * sms);
+    const int iters = 2048, threads = 1024;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    float ms = 0.f;
+    for (int rep = 0; rep < 2; rep++) {
+        cudaEventRecord(e0);
+        if (width == 16) k_lds_rate<16><<<sms, threads>>>(out, cyc, iters, pattern);
+        else if (width == 8) k_lds_rate<8><<<sms, threads>>>(out, cyc, iters, pattern);
+        else k_lds_rate<4><<<sms, threads>>>(out, cyc, iters, pattern);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+    }
+    cudaDeviceSynchronize();
+    if (getenv("ASW_UBENCH_WALL")) {   // wall-clock view: ns per warp-level load per SM (includes launch + fill overhead)
+        cudaFree(out);
+        cudaFree(cyc);
+        return (double)ms * 1e6 / ((double)iters * 16 * (threads / 32));
+    }
+    long long h[1024];
+    cudaMemcpy(h, cyc, sizeof(long long) * sms, cudaMemcpyDeviceToHost);
+    cudaFree(out);
+    cudaFree(cyc);
+    if (cudaGetLastError() != cudaSuccess) return -1.0;
+    double sum = 0;
+    for (int i = 0; i < sms; i++) sum += (double)h[i];
+    return sum / sms / ((double)iters * 16 * (threads / 32));   // cycles per warp-level load, per SM
+}
+
 
 // Sustained FP32 FMA throughput in TFLOP/s (2 flop per FMA), dependent chains with ILP 8.
 UB_API double asw_ubench_ffma_tflops(int packed) {
