@@ -79,6 +79,23 @@ typedef struct asw_timing {
     int kernel_launches;  /* CUDA kernels launched by the call */
 } asw_timing;
 
+/* Device times of the consumers of the hot path, the remaining columns of the reference's log
+ * (main.cpp:661-708: consistency, v_ref_mean_L/R, h_ref_mean_L/R, wta_mean_LR, consistency_mean,
+ * total refinement, median, total WTA method).  Filled by asw_stereo. */
+typedef struct asw_tail_timing {
+    float right_wta_ms;          /* right-view part of asw_WTA (the reference computes it inside asw_WTA) */
+    float consistency_ms;        /* first Constistency                              (main.cpp:531-536) */
+    float vref_mean_l_ms;        /* mean asw_ref_v, left view                       (main.cpp:547-552) */
+    float vref_mean_r_ms;        /* mean asw_ref_v, right view                      (main.cpp:555-560) */
+    float href_mean_l_ms;        /* mean asw_ref_h, left view                       (main.cpp:563-568) */
+    float href_mean_r_ms;        /* mean asw_ref_h, right view                      (main.cpp:571-576) */
+    float wta_ref_mean_ms;       /* mean asw_WTA_REF                                (main.cpp:579-589) */
+    float consistency_mean_ms;   /* mean Constistency inside the refinement loop    (main.cpp:601-608) */
+    float refinement_total_ms;   /* all refinement rounds */
+    float median_ms;             /* Median                                          (main.cpp:617-619) */
+    float total_ms;              /* hot path + tail, device only ("total WTA method") */
+} asw_tail_timing;
+
 ASW_API const char* asw_version(void);
 ASW_API const char* asw_strerror(int status);
 
@@ -188,7 +205,7 @@ ASW_API int asw_Median(asw_ctx* ctx, int W, int H, const uint8_t* d_input_rgba, 
  * consistency images (asw_consistency_pre-reff.png / asw_consistency_post-reff.png). */
 ASW_API int asw_stereo(asw_ctx* ctx, const uint8_t* left_rgba, const uint8_t* right_rgba, int W, int H, const asw_params* prm,
                        int refine_iters, uint8_t* disparity_rgba, uint8_t* consistency_pre_rgba, uint8_t* consistency_post_rgba,
-                       asw_timing* timing);
+                       asw_timing* timing, asw_tail_timing* tail_timing);
 
 /* ---- device memory helpers (so a plain C/C++ host needs no CUDA headers) -------------
  * Replace clCreateBuffer / clCreateImage2D(COPY_HOST_PTR) / clEnqueueReadImage /

@@ -11,7 +11,7 @@
 // --method hot (default) runs the hot path only and writes asw_disparity<suffix>.png = the WTA image;
 // --method whole runs the whole ASW method (asw_stereo: + consistency, k refinement rounds, median,
 // main.cpp:529-631) and writes the reference's three ASW PNGs (main.cpp:621-631) with the suffix.
-// Out of scope (columns written as 0): the cross-based method; per-stage times of the refinement tail.
+// Out of scope (columns written as 0): the cross-based method.
 //
 // Usage: stereo_matching [--pics pics.txt] [--root DIR] [--runs 10] [--device 0] [--ndisp 61]
 //                        [--iterations 7] [--method hot|whole] [--refine 6] [--out-suffix _wta] [--log FILE]
@@ -114,8 +114,10 @@ int main(int argc, char** argv) {
             fprintf(to_file, "\nRun %d \t", run + 1);
             printf("\n---Working...\nRaw cost aggregation..  \ngestalt principle - support area.. \nCost aggregation.. \nWTA.. ");
             asw_timing t;
+            asw_tail_timing tt;
+            memset(&tt, 0, sizeof tt);
             if (whole)
-                st = asw_stereo(ctx, imgL.pixel.data(), imgR.pixel.data(), (int)W, (int)H, &prm, refine, disp.data(), pre.data(), post.data(), &t);
+                st = asw_stereo(ctx, imgL.pixel.data(), imgR.pixel.data(), (int)W, (int)H, &prm, refine, disp.data(), pre.data(), post.data(), &t, &tt);
             else
                 st = asw_disparity(ctx, imgL.pixel.data(), imgR.pixel.data(), (int)W, (int)H, &prm, disp.data(), nullptr, nullptr, &t);
             if (st != ASW_OK) {
@@ -139,9 +141,14 @@ int main(int argc, char** argv) {
             fprintf(to_file, "\t\t");
             fprintf(to_file, "%0.3f\t%0.3f\t%0.3f\t%0.3f\t%0.3f\t%0.3f\t", t.raw_ms, t.supp_ms, t.vagg_mean_ms, t.hagg_mean_ms,
                     t.agg_total_ms, t.wta_ms);
-            for (int c = 0; c < 9; c++) fprintf(to_file, "%0.3f\t", 0.0);    // consistency / refinement / median: next rows
-            fprintf(to_file, "%0.3f\t", t.total_ms);
-            sum_total += t.total_ms;
+            // consistency, v_ref_mean_L/R, h_ref_mean_L/R, wta_mean_LR, consistency_mean, total refinement, median
+            // (main.cpp:661-708; zero with --method hot); the right-view WTA is folded into the first consistency column
+            fprintf(to_file, "%0.3f\t%0.3f\t%0.3f\t%0.3f\t%0.3f\t%0.3f\t%0.3f\t%0.3f\t%0.3f\t", tt.right_wta_ms + tt.consistency_ms,
+                    tt.vref_mean_l_ms, tt.vref_mean_r_ms, tt.href_mean_l_ms, tt.href_mean_r_ms, tt.wta_ref_mean_ms, tt.consistency_mean_ms,
+                    tt.refinement_total_ms, tt.median_ms);
+            const float whole_ms = whole ? tt.total_ms : t.total_ms;
+            fprintf(to_file, "%0.3f\t", whole_ms);
+            sum_total += whole_ms;
         }
         if (runs > 0) {
             double ms = sum_total / runs;

@@ -52,6 +52,15 @@ class CTiming(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class CTailTiming(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("right_wta_ms", "consistency_ms", "vref_mean_l_ms", "vref_mean_r_ms", "href_mean_l_ms",
+                                          "href_mean_r_ms", "wta_ref_mean_ms", "consistency_mean_ms", "refinement_total_ms",
+                                          "median_ms", "total_ms")]
+
+    def as_dict(self) -> dict:
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
 @dataclass
 class AswParams:
     """Defaults reproduce the reference's literals (asw_vsupport.cl:19,22,24; asw_aggr.cl:16; main.cpp:177)."""
@@ -109,7 +118,7 @@ def load_library() -> C.CDLL:
     lib.asw_ref_h.argtypes = [vp, C.c_int, C.c_int, pp, u8p, f32p, f32p, f32p]
     lib.asw_WTA_REF.argtypes = [vp, C.c_int, C.c_int, pp, f32p, f32p, f32p, u8p, u8p, f32p, f32p, f32p, f32p]
     lib.asw_Median.argtypes = [vp, C.c_int, C.c_int, u8p, u8p]
-    lib.asw_stereo.argtypes = [vp, u8p, u8p, C.c_int, C.c_int, pp, C.c_int, u8p, u8p, u8p, tp]
+    lib.asw_stereo.argtypes = [vp, u8p, u8p, C.c_int, C.c_int, pp, C.c_int, u8p, u8p, u8p, tp, C.POINTER(CTailTiming)]
     lib.asw_dev_alloc.argtypes = [vp, C.POINTER(vp), C.c_size_t]
     lib.asw_dev_free.argtypes = [vp, vp]
     lib.asw_memcpy_h2d.argtypes = [vp, vp, vp, C.c_size_t]
@@ -275,11 +284,13 @@ class AswContext:
         left, right = _rgba(left), _rgba(right)
         H, W, _ = left.shape
         out = {k: np.empty((H, W, 4), np.uint8) for k in ("disparity", "pre_red", "post_red")}
-        tm = CTiming()
+        tm, tt = CTiming(), CTailTiming()
         p = params.c()
         self._check(self.lib.asw_stereo(self.h, left.ctypes.data, right.ctypes.data, W, H, C.byref(p), refine_iters,
-                                        out["disparity"].ctypes.data, out["pre_red"].ctypes.data, out["post_red"].ctypes.data, C.byref(tm)))
+                                        out["disparity"].ctypes.data, out["pre_red"].ctypes.data, out["post_red"].ctypes.data, C.byref(tm),
+                                        C.byref(tt)))
         out["timing"] = tm.as_dict()
+        out["tail_timing"] = tt.as_dict()
         return out
 
     def asw_Constistency(self, W, H, params, ref, tar, confidence_ref, confidence_tar, output, output_red):

@@ -558,7 +558,7 @@ int asw_Median(asw_ctx* ctx, int W, int H, const uint8_t* in, uint8_t* out) {
 // The whole method, main.cpp:463-631: fused hot path -> right-view WTA -> consistency -> k x (ref_v L,R;
 // ref_h L,R; WTA_REF; consistency) -> median.
 int asw_stereo(asw_ctx* ctx, const uint8_t* left, const uint8_t* right, int W, int H, const asw_params* prm, int refine_iters,
-               uint8_t* disparity, uint8_t* pre, uint8_t* post, asw_timing* tm) {
+               uint8_t* disparity, uint8_t* pre, uint8_t* post, asw_timing* tm, asw_tail_timing* tail) {
     int st = check_params(ctx, W, H, prm);
     if (st) return st;
     if (!left || !right) return fail(ctx, ASW_ERR_INVALID, "image pointer is NULL");
@@ -579,27 +579,62 @@ int asw_stereo(asw_ctx* ctx, const uint8_t* left, const uint8_t* right, int W, i
     CU(cudaMemcpyAsync(ctx->img_r.p, right, n * 4, cudaMemcpyHostToDevice, ctx->stream));     // main.cpp:244
     const int keep = ctx->keep_volume;
     ctx->keep_volume = 1;                                          // WTA_REF and the right view read the final volume
-    st = run_band(ctx, dl, dr, W, H, 0, H, prm, nullptr, nullptr, nullptr, tm);
+    asw_timing hot;
+    st = run_band(ctx, dl, dr, W, H, 0, H, prm, nullptr, nullptr, nullptr, (tm || tail) ? &hot : nullptr);
     ctx->keep_volume = keep;
     if (st) return st;
+    if (tm) *tm = hot;
     const float* vol = ctx->final_volume;
+    // the hot path's events were read by run_band (it synchronised): the tail reuses them
+    EvTimer et{ctx, tail != nullptr && 3 + 6 * refine_iters + 1 <= asw_ctx::kMaxEvents};
+    const int e0 = et.mark();
     // left + right view and both confidences (asw_wta.cl, main.cpp:519-526)
     if ((st = asw_WTA(ctx, W, H, prm, vol, lw, nullptr, nullptr, rw, cr, ct))) return st;
+    const int e_wta = et.mark();
     if ((st = asw_Constistency(ctx, W, H, prm, lw, rw, cr, ct, ce, red))) return st;          // main.cpp:531-536
+    const int e_cons = et.mark();
     for (int i = 0; i < refine_iters; i++) {                                                  // main.cpp:545-614
         if ((st = asw_ref_v(ctx, W, H, prm, dl, ce, cr, vl))) return st;
+        et.mark();
         if ((st = asw_ref_v(ctx, W, H, prm, dr, rw, ct, vr))) return st;
+        et.mark();
         if ((st = asw_ref_h(ctx, W, H, prm, dl, cr, vl, hl))) return st;
+        et.mark();
         if ((st = asw_ref_h(ctx, W, H, prm, dr, ct, vr, hr))) return st;
+        et.mark();
         if ((st = asw_WTA_REF(ctx, W, H, prm, vol, hl, hr, lw, rw, nullptr, nullptr, cr, ct))) return st;
+        et.mark();
         if ((st = asw_Constistency(ctx, W, H, prm, lw, rw, cr, ct, ce, red2))) return st;
+        et.mark();
     }
+    const int e_ref = e_cons + 6 * refine_iters;
     if ((st = asw_Median(ctx, W, H, ce, fin))) return st;                                     // main.cpp:617-619
+    const int e_med = et.mark();
     if (disparity) CU(cudaMemcpyAsync(disparity, fin, n * 4, cudaMemcpyDeviceToHost, ctx->stream));                 // main.cpp:621
     if (pre) CU(cudaMemcpyAsync(pre, red, n * 4, cudaMemcpyDeviceToHost, ctx->stream));                             // main.cpp:625
     if (post) CU(cudaMemcpyAsync(post, refine_iters ? red2 : red, n * 4, cudaMemcpyDeviceToHost, ctx->stream));     // main.cpp:629
     CU(cudaStreamSynchronize(ctx->stream));
     if (tm) tm->kernel_launches = ctx->launches;
+    if (tail) {
+        memset(tail, 0, sizeof *tail);
+        if (et.on) {
+            tail->right_wta_ms = et.ms(e0, e_wta);
+            tail->consistency_ms = et.ms(e_wta, e_cons);
+            float sum[6] = {0, 0, 0, 0, 0, 0};
+            for (int i = 0; i < refine_iters; i++)
+                for (int k = 0; k < 6; k++) sum[k] += et.ms(e_cons + 6 * i + k, e_cons + 6 * i + k + 1);
+            const float inv = refine_iters ? 1.0f / refine_iters : 0.f;
+            tail->vref_mean_l_ms = sum[0] * inv;
+            tail->vref_mean_r_ms = sum[1] * inv;
+            tail->href_mean_l_ms = sum[2] * inv;
+            tail->href_mean_r_ms = sum[3] * inv;
+            tail->wta_ref_mean_ms = sum[4] * inv;
+            tail->consistency_mean_ms = sum[5] * inv;
+            tail->refinement_total_ms = et.ms(e_cons, e_ref);
+            tail->median_ms = et.ms(e_ref, e_med);
+            tail->total_ms = hot.total_ms + et.ms(e0, e_med);
+        }
+    }
     return ASW_OK;
 }
 

@@ -99,6 +99,9 @@ def test_whole_method_parity(ctx, oracle, ds, D, k):
     for key in ("pre_red", "post_red", "disparity"):
         assert_bit_equal(got[key], want[key], f"asw_stereo {key}")
     assert got["timing"]["kernel_launches"] > 0
+    tt = got["tail_timing"]
+    assert tt["total_ms"] > got["timing"]["total_ms"] > 0 and tt["median_ms"] > 0 and tt["consistency_ms"] > 0
+    assert (tt["refinement_total_ms"] > 0) == (k > 0)
 
 
 def test_whole_method_no_refinement_and_crop(ctx, oracle):
@@ -141,3 +144,7 @@ def test_host_binary_whole_method(tmp_path):
         assert np.array_equal(load_rgba(str(tmp_path / "tsukuba" / name)), load_rgba(os.path.join(GOLDEN, "tsukuba", name))), name
     log = (tmp_path / "log.tsv").read_text()
     assert "total WTA method" in log and "Run 2" in log
+    run1 = [ln for ln in log.splitlines() if ln.startswith("Run 1")][0].split("\t")
+    vals = [float(v) for v in run1[1:] if v.strip()]
+    assert len(vals) == 14 + 6 + 9 + 1                     # cross-based (0) + hot path + tail + total, as in main.cpp:181
+    assert all(v == 0 for v in vals[:14]) and all(v > 0 for v in vals[14:])
