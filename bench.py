@@ -187,9 +187,13 @@ def main():
     units_per_step_rank = W * out_rows * D * len(pairs)              # pix*disp this rank produces per step
     torch.cuda.synchronize()
 
+    stage_log = []   # per-stage CUDA-event times of every hot-path call made inside the timed region
+
     def step_device():
         for (l, rr), o in zip(dev_in, dev_d):
-            ctx.disparity_raw(l.data_ptr(), rr.data_ptr(), W, H, params, None, o.data_ptr(), None, band=band)
+            # timing=True: the library brackets every kernel group with events on its own stream (and waits for
+            # them at the end of the call, a ~20 us host gap per call that stays inside the timed region)
+            stage_log.append(ctx.disparity_raw(l.data_ptr(), rr.data_ptr(), W, H, params, None, o.data_ptr(), None, timing=True, band=band))
         if world > 1:   # the single collective: all-gather of the uint8 disparity maps / bands
             with torch.cuda.stream(stream):
                 if band_mode and H % world == 0:
@@ -240,6 +244,7 @@ def main():
         sampler.start()
     ms_dev = timed(step_device, args.steps, max(args.warmup, 3))
     clocks = sampler.stop() if rank == 0 else None
+    timed_calls = stage_log[-args.steps * len(pairs):]           # the calls of the timed region (warm-up calls dropped)
     ms_host = timed(step_host, args.steps, 1)
 
     total_units = units_per_step_rank
@@ -251,9 +256,8 @@ def main():
     e2e_value = total_units * args.steps / (ms_host * 1e-3) / 1e6
 
     # ---- per-stage timing of one instrumented step (outside the timed region) ----------------------
-    tm = ctx.disparity_raw(dev_in[0][0].data_ptr(), dev_in[0][1].data_ptr(), W, H, params, None, dev_d[0].data_ptr(), None,
-                           timing=True, band=band)
-    launches_per_pair = tm["kernel_launches"]
+    tm = {k: float(np.mean([c[k] for c in timed_calls])) for k in timed_calls[0]}
+    launches_per_pair = int(timed_calls[0]["kernel_launches"])
 
     if rank == 0:
         # roofline of the dominant kernel: F_alg of one pass = 4*T*W*rows*D, over its mean duration
@@ -261,8 +265,14 @@ def main():
         if band_mode:   # halo rows computed per pass, averaged over the r iterations
             rows_mean = float(np.mean([min(H, band[1] + (r - 1 - it) * 16) - max(0, band[0] - (r - 1 - it) * 16) for it in range(r)]))
         pass_flops = 4.0 * T_TAPS * W * rows_mean * D
-        v_ms, h_ms = tm["vagg_mean_ms"], tm["hagg_mean_ms"]
-        dom, dom_ms = ("asw_vCostAggregation (k_vagg_t)", v_ms) if v_ms >= h_ms else ("asw_hCostAggregation (k_hagg_t)", h_ms)
+        # V pass = main kernel + two small launches (diagonal fix-up, edge padding): the dominant KERNEL is the main one
+        v_ms, h_ms = tm["vagg_mean_ms"] - tm["vfix_mean_ms"], tm["hagg_mean_ms"]
+        tma = args.family == 0 and ((D + 31) // 32 * 32) % 128 == 0
+        v_name = "k_vagg_v2 (asw_vCostAggregation; mean of its %d launches per frame)" % r if tma else "k_vagg_t (asw_vCostAggregation)"
+        h_name = "k_hagg_split (asw_hCostAggregation)" if tma else "k_hagg_t (asw_hCostAggregation)"
+        dom, dom_ms = (v_name, v_ms) if v_ms >= h_ms else (h_name, h_ms)
+        if v_ms >= h_ms and tma:
+            pass_flops *= (D - 1.5) / D                         # the fix-up launch produces 1.5 of the D outputs per pixel
         peak, peak_src = FP32_PEAK_FALLBACK_TFLOPS, "computed: 148 SMs x 128 lanes x 2 x 1.965 GHz (MEASURED_PEAKS.json has no FP32 figure)"
         ffma = None
         try:
@@ -276,8 +286,17 @@ def main():
         hbm_peak = json.load(open(peaks_file)).get("hbm_gbs") if os.path.exists(peaks_file) else 6650.0
         Dp = (D + 31) // 32 * 32
         pass_bytes = 3.0 * 4 * W * rows_mean * Dp      # tiled kernels: read cost + read denominator + write cost
-        roofline = {"bound": "fp32", "kernel": dom.replace("k_vagg_t", "k_vagg_v2 + fix-up/pad launches").replace("k_hagg_t", "k_hagg_v2"), "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": peak_src, "measured_ffma_microbench": ffma,
+        traffic, traffic_src = None, None                       # DRAM bytes per launch of that kernel, from the committed ncu --set full capture
+        tfiles = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_traffic.json")) if os.path.isdir(os.path.join(ROOT, "profiles")) else []
+        if tfiles and args.workload == "cfg3" and world == 1:
+            tj = json.load(open(os.path.join(ROOT, "profiles", tfiles[-1])))
+            key = "k_vagg_v2" if v_ms >= h_ms else "k_hagg_split"
+            if key in tj:
+                traffic, traffic_src = tj[key]["dram_bytes_per_launch"], "profiles/" + tfiles[-1]
+        roofline = {"bound": "fp32", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                    "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": pass_bytes,
+                    "timing": "CUDA events on the library's stream around every launch group, mean over the timed region",
+                    "peak_source": peak_src, "measured_ffma_microbench": ffma,
                     "whole_path_frac": alg_flops(W, rows_mean, D, r) / (tm["total_ms"] * 1e-3) / 1e12 / peak,
                     "v_pass_ms": v_ms, "h_pass_ms": h_ms,
                     "hbm": {"algorithmic_gbs": pass_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0, "peak_gbs": hbm_peak,
@@ -300,7 +319,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "Mpix*disp/s", "h2d_bytes_per_step": int(npx_in), "d2h_bytes_per_step": int(W * out_rows * len(pairs)),
                     "ms_per_step": ms_host / args.steps},
             "gpu_launches": int(launches_per_pair * len(pairs) * args.steps),
-            "stage_ms": {k: tm[k] for k in ("raw_ms", "supp_ms", "vagg_mean_ms", "hagg_mean_ms", "agg_total_ms", "wta_ms", "total_ms")},
+            "stage_ms": {k: tm[k] for k in ("raw_ms", "supp_ms", "vagg_mean_ms", "vfix_mean_ms", "hagg_mean_ms", "agg_total_ms", "wta_ms", "total_ms")},
             "roofline": roofline,
             "cpu_baseline": cpu,
         }

@@ -77,6 +77,8 @@ typedef struct asw_timing {
     float h2d_ms;         /* host->device upload (host-buffer entry points only) */
     float d2h_ms;         /* device->host download */
     int kernel_launches;  /* CUDA kernels launched by the call */
+    float vfix_mean_ms;   /* part of vagg_mean_ms spent in the small fix-up / edge-padding launches that follow the
+                             main vertical kernel (0 for kernel families that have none) */
 } asw_timing;
 
 /* Device times of the consumers of the hot path, the remaining columns of the reference's log

@@ -32,6 +32,24 @@ if os.path.exists(rep):
     txt = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_summary.py"), raw], capture_output=True, text=True).stdout
     open(os.path.join(P, f"{tag}_ncu_full_summary.txt"), "w").write(
         "# ncu --set full --clock-control none, one cfg3 frame (1800x1500x256, r=2): V/H aggregation kernels, FIRST and steady-state launches\n" + txt)
+    # DRAM traffic per launch of the steady-state aggregation kernels (bench.py reports it as roofline.traffic)
+    rows = list(csv.reader(open(raw)))
+    hd = {n: i for i, n in enumerate(rows[0])}
+    traffic = {}
+    for r in rows[2:]:
+        name = r[hd["Kernel Name"]]
+        key = "k_vagg_v2" if "k_vagg_v2<8, 0>" in name or "k_vagg_v2<(int)8, (bool)0>" in name else \
+              "k_hagg_split" if "k_hagg_split<0>" in name or "k_hagg_split<(bool)0>" in name else None
+        if key:
+            def gb(col):
+                v, u = float(r[hd[col]].replace(",", "")), rows[1][hd[col]]
+                return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[u]
+            rd, wr = gb("dram__bytes_read.sum"), gb("dram__bytes_write.sum")
+            traffic[key] = {"kernel": name.split("(")[0], "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_launch": rd + wr,
+                            "duration_ms_under_ncu": float(r[hd["gpu__time_duration.sum"]].replace(",", "")) * {"ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}.get(rows[1][hd["gpu__time_duration.sum"]], 1.0),
+                            "source": f"ncu --set full --clock-control none on one cfg3 frame; summary in profiles/{tag}_ncu_full_summary.txt"}
+    if traffic:
+        json.dump(traffic, open(os.path.join(P, f"{tag}_traffic.json"), "w"), indent=1)
 for f, d in (("ubench.json", f"{tag}_ubench.json"), ("bench_cfg3.json", f"{tag}_bench_cfg3.json"), ("bench_reference.json", f"{tag}_bench_reference.json"),
              ("pytest_gpu.log", f"{tag}_pytest_gpu.log"), ("smoke.log", f"{tag}_smoke.log")):
     if os.path.exists(os.path.join(G, f)):

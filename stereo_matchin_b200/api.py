@@ -46,7 +46,7 @@ class CParams(C.Structure):
 class CTiming(C.Structure):
     _fields_ = [("raw_ms", C.c_float), ("supp_ms", C.c_float), ("vagg_mean_ms", C.c_float), ("hagg_mean_ms", C.c_float),
                 ("agg_total_ms", C.c_float), ("wta_ms", C.c_float), ("total_ms", C.c_float), ("h2d_ms", C.c_float),
-                ("d2h_ms", C.c_float), ("kernel_launches", C.c_int)]
+                ("d2h_ms", C.c_float), ("kernel_launches", C.c_int), ("vfix_mean_ms", C.c_float)]
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -46,7 +46,7 @@ struct asw_ctx {
     Scratch vol_ref;                       // final volume in the reference layout (keep_volume)
     Scratch fimg_l, fimg_r;                // images as float4 (r, g, b, 0), sampler conversion applied
     Scratch tail[12];                      // whole-method buffers (asw_stereo)
-    enum { kMaxEvents = 64 };
+    enum { kMaxEvents = 96 };
     cudaEvent_t ev[kMaxEvents] = {};
 };
 
@@ -158,18 +158,24 @@ struct StageTimes {
     EvTimer et;
     int e_start = -1, e_raw = -1, e_supp = -1, e_agg = -1, e_wta = -1;
     bool pass_marks = false;
+    int ev_v0[24], ev_vmain[24], ev_v1[24], ev_h1[24];   // per iteration: V start, V main kernel end, V end, H end
+    int prev = -1;                                       // the latest mark
+    void v_begin(int it) { if (pass_marks) { ev_v0[it] = prev; ev_vmain[it] = -1; } }
+    void v_end(int it) { if (pass_marks) prev = ev_v1[it] = et.mark(); }
+    void h_end(int it) { if (pass_marks) prev = ev_h1[it] = et.mark(); }
     void fill(asw_timing* tm, int r, int launches) {
         memset(tm, 0, sizeof *tm);
         tm->raw_ms = et.ms(e_start, e_raw);
         tm->supp_ms = et.ms(e_raw, e_supp);
-        float vsum = 0.f, hsum = 0.f;
-        for (int it = 0; pass_marks && it < r; it++) {   // marks after e_supp alternate V, H
-            const int ev_v = e_supp + 1 + 2 * it;
-            vsum += et.ms(ev_v - 1, ev_v);
-            hsum += et.ms(ev_v, ev_v + 1);
+        float vsum = 0.f, hsum = 0.f, fsum = 0.f;
+        for (int it = 0; pass_marks && it < r; it++) {
+            vsum += et.ms(ev_v0[it], ev_v1[it]);
+            hsum += et.ms(ev_v1[it], ev_h1[it]);
+            if (ev_vmain[it] >= 0) fsum += et.ms(ev_vmain[it], ev_v1[it]);
         }
         tm->vagg_mean_ms = r ? vsum / r : 0.f;
         tm->hagg_mean_ms = r ? hsum / r : 0.f;
+        tm->vfix_mean_ms = r ? fsum / r : 0.f;
         tm->agg_total_ms = et.ms(e_supp, e_agg);
         tm->wta_ms = et.ms(e_agg, e_wta);
         tm->total_ms = et.ms(e_start, e_wta);
@@ -230,14 +236,20 @@ int run_band(asw_ctx* ctx, const uint8_t* dl, const uint8_t* dr, int W, int H, i
         CUL(launch_support_v2(s, false, false, fl, tl, ya, yb, p->gamma_c, p->gamma_p, hL));
         CUL(launch_support_v2(s, true, true, fr, tl, ya, yb, p->gamma_c, p->gamma_p, vR));
         CUL(launch_support_v2(s, false, true, fr, tl, ya, yb, p->gamma_c, p->gamma_p, hR));
-        t.e_supp = t.et.mark();
+        t.prev = t.e_supp = t.et.mark();
         for (int it = 0; it < r; it++) {
             const int ylo = max(ya, y0 - (r - 1 - it) * R), yhi = min(yb, y1 + (r - 1 - it) * R);
-            CUL(launch_vagg_v2(s, it == 0, tl, ylo, yhi, vL, vR, va, den_v, vb));
+            cudaEvent_t ev_main = nullptr;
+            t.v_begin(it);
+            if (t.pass_marks && t.et.on && t.et.n < asw_ctx::kMaxEvents) {   // an event between the main kernel and its fix-up / padding launches
+                t.ev_vmain[it] = t.et.n++;
+                ev_main = ctx->ev[t.ev_vmain[it]];
+            }
+            CUL(launch_vagg_v2(s, it == 0, tl, ylo, yhi, vL, vR, va, den_v, vb, ev_main));
             ctx->launches += 2;                                // main kernel + diagonal fix-up + edge padding kernels
-            if (t.pass_marks) t.et.mark();
+            t.v_end(it);
             CUL(launch_hagg_v2(s, it == 0, tl, ylo, yhi, hL, hR, vb, den_h, va));
-            if (t.pass_marks) t.et.mark();
+            t.h_end(it);
         }
         t.e_agg = t.et.mark();
         CUL(launch_wta_v2(s, tl, y0, y1, y0, va, d_rgba, d_d, d_conf));
@@ -257,14 +269,15 @@ int run_band(asw_ctx* ctx, const uint8_t* dl, const uint8_t* dr, int W, int H, i
         CUL(launch_support_t(s, false, dl, b, ya, yb, p->gamma_c, p->gamma_p, hL));
         CUL(launch_support_t(s, true, dr, b, ya, yb, p->gamma_c, p->gamma_p, vR));
         CUL(launch_support_t(s, false, dr, b, ya, yb, p->gamma_c, p->gamma_p, hR));
-        t.e_supp = t.et.mark();
+        t.prev = t.e_supp = t.et.mark();
         // V reads va, writes vb; H reads vb, writes va (its input was consumed by V already).
         for (int it = 0; it < r; it++) {
             const int ylo = max(ya, y0 - (r - 1 - it) * R), yhi = min(yb, y1 + (r - 1 - it) * R);
+            t.v_begin(it);
             CUL(launch_vagg_t(s, it == 0, b, ylo, yhi, D, vL, vR, va, den_v, vb));
-            if (t.pass_marks) t.et.mark();
+            t.v_end(it);
             CUL(launch_hagg_t(s, it == 0, b, ylo, yhi, D, hL, hR, vb, den_h, va));
-            if (t.pass_marks) t.et.mark();
+            t.h_end(it);
         }
         t.e_agg = t.et.mark();
         CUL(launch_wta_t(s, b, y0, y1, y0, D, va, d_rgba, d_d, d_conf));
@@ -283,14 +296,15 @@ int run_band(asw_ctx* ctx, const uint8_t* dl, const uint8_t* dr, int W, int H, i
         if ((st = launch_support(ctx, false, dl, b, ya, yb, p, hL))) return st;           // :474-476
         if ((st = launch_support(ctx, true, dr, b, ya, yb, p, vR))) return st;            // :478-480
         if ((st = launch_support(ctx, false, dr, b, ya, yb, p, hR))) return st;           // :482-484
-        t.e_supp = t.et.mark();
+        t.prev = t.e_supp = t.et.mark();
         const float* in = raw;
         for (int it = 0; it < r; it++) {                                                  // main.cpp:492-515
             const int ylo = max(ya, y0 - (r - 1 - it) * R), yhi = min(yb, y1 + (r - 1 - it) * R);
+            t.v_begin(it);
             if ((st = launch_agg_basic(ctx, true, b, ylo, yhi, p, vL, vR, in, nullptr, va))) return st;
-            if (t.pass_marks) t.et.mark();
+            t.v_end(it);
             if ((st = launch_agg_basic(ctx, false, b, ylo, yhi, p, hL, hR, va, nullptr, hb))) return st;
-            if (t.pass_marks) t.et.mark();
+            t.h_end(it);
             in = hb;
         }
         t.e_agg = t.et.mark();
