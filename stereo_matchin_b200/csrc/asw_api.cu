@@ -246,7 +246,7 @@ int run_band(asw_ctx* ctx, const uint8_t* dl, const uint8_t* dr, int W, int H, i
                 ev_main = ctx->ev[t.ev_vmain[it]];
             }
             CUL(launch_vagg_v2(s, it == 0, tl, ylo, yhi, vL, vR, va, den_v, vb, ev_main));
-            ctx->launches += 2;                                // main kernel + diagonal fix-up + edge padding kernels
+            ctx->launches += kVHelpers ? 1 : 2;                // main kernel (+ diagonal fix-up kernel) + edge padding kernel
             t.v_end(it);
             CUL(launch_hagg_v2(s, it == 0, tl, ylo, yhi, hL, hR, vb, den_h, va));
             t.h_end(it);
