@@ -198,9 +198,9 @@ int run_band(asw_ctx* ctx, const uint8_t* dl, const uint8_t* dr, int W, int H, i
     const int ya = max(0, y0 - r * R), yb = min(H, y1 + r * R);
     Band b{W, H, ya, yb - ya};
     const bool tma = ctx->family == 0 && tma_supported(R, D);
-    const bool tiled = !tma && ctx->family == 0 && tiled_supported(R);
+    const bool tiled = !tma && (ctx->family == 0 || ctx->family == 2) && tiled_supported(R);
     const TL tl = make_tl(b, D);
-    const int Dp = (tiled || tma) ? padded_D(D) : D;
+    const int Dp = tma ? tma_padded_D(D) : tiled ? padded_D(D) : D;
     const size_t vol_bytes = sizeof(float) * (tma ? tl.vol_elems() : b.plane() * (size_t)Dp);
     const size_t tab_bytes = sizeof(float) * b.plane() * (size_t)T;
     int st;
@@ -407,7 +407,7 @@ int asw_device_info(asw_ctx* ctx, int* sm_count, int* sm_clock_khz, size_t* tota
 }
 
 int asw_set_kernel_family(asw_ctx* ctx, int family) {
-    if (!ctx || family < 0 || family > 1) return ASW_ERR_INVALID;
+    if (!ctx || family < 0 || family > 2) return ASW_ERR_INVALID;
     ctx->family = family;
     return ASW_OK;
 }
