@@ -69,6 +69,18 @@ def lib() -> C.CDLL:
         _lib.oracle_median.argtypes = [u8p, C.c_int, C.c_int, u8p]
         _lib.oracle_asw_full.restype = C.c_int
         _lib.oracle_asw_full.argtypes = [u8p, u8p, C.c_int, C.c_int, C.POINTER(_Params), C.c_int, C.c_int, u8p, u8p, u8p]
+        i32p = C.c_void_p
+        _lib.oracle_cb_median_grid.argtypes = [u8p, C.c_int, C.c_int, C.c_int, u8p]
+        _lib.oracle_cb_cross.argtypes = [u8p, C.c_int, C.c_int, C.c_int, i32p]
+        _lib.oracle_cb_aggregation.argtypes = [u8p, u8p, C.c_int, C.c_int, C.c_int, f32p]
+        _lib.oracle_cb_integral_h.argtypes = [f32p, C.c_int, C.c_int, C.c_int]
+        _lib.oracle_cb_integral_v.argtypes = [f32p, C.c_int, C.c_int, C.c_int]
+        _lib.oracle_cb_oii_hcross.argtypes = [i32p, i32p, f32p, C.c_int, C.c_int, C.c_int, f32p]
+        _lib.oracle_cb_oii_vcross.argtypes = [i32p, i32p, f32p, C.c_int, C.c_int, C.c_int, f32p]
+        _lib.oracle_cb_init_disparity.argtypes = [f32p, C.c_int, C.c_int, C.c_int, u8p]
+        _lib.oracle_cb_disparity.argtypes = [u8p, i32p, C.c_int, C.c_int, C.c_int, u8p]
+        _lib.oracle_cross_full.restype = C.c_int
+        _lib.oracle_cross_full.argtypes = [u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u8p, u8p, u8p]
         _lib.oracle_asw_hot_path.restype = C.c_int
         _lib.oracle_asw_hot_path.argtypes = [u8p, u8p, C.c_int, C.c_int, C.POINTER(_Params), C.c_int,
                                              f32p, u8p, u8p, f32p, f32p, f32p, f32p]
@@ -229,4 +241,77 @@ def asw_full(left, right, params: OracleParams | None = None, use_fma: bool = Fa
                                _u8(r["pre_red"]), _u8(r["post_red"]))
     if rc != 0:
         raise RuntimeError(f"oracle_asw_full failed rc={rc}")
+    return r
+
+
+# ---- the cross-based method (cross_oracle.c) ---------------------------------------------------------
+
+def _i32(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def cb_median_grid(img_rgba, local: int = 3) -> np.ndarray:
+    img_rgba = _img(img_rgba)
+    H, W, _ = img_rgba.shape
+    out = np.empty_like(img_rgba)
+    lib().oracle_cb_median_grid(_u8(img_rgba), W, H, local, _u8(out))
+    return out
+
+
+def cb_cross(img_rgba, max_arm: int = 25) -> np.ndarray:
+    img_rgba = _img(img_rgba)
+    H, W, _ = img_rgba.shape
+    out = np.empty((4, H, W), np.int32)
+    lib().oracle_cb_cross(_u8(img_rgba), W, H, max_arm, _i32(out))
+    return out
+
+
+def cb_aggregation(left, right, D: int = 61) -> np.ndarray:
+    left, right = _img(left), _img(right)
+    H, W, _ = left.shape
+    cost = np.empty((D, H, W), np.float32)
+    lib().oracle_cb_aggregation(_u8(left), _u8(right), W, H, D, _f32(cost))
+    return cost
+
+
+def cb_integral(cost, horizontal: bool) -> np.ndarray:
+    out = np.array(cost, np.float32, order="C", copy=True)
+    D, H, W = out.shape
+    (lib().oracle_cb_integral_h if horizontal else lib().oracle_cb_integral_v)(_f32(out), W, H, D)
+    return out
+
+
+def cb_oii(cross_l, cross_r, integral, horizontal: bool) -> np.ndarray:
+    cross_l, cross_r = np.ascontiguousarray(cross_l, np.int32), np.ascontiguousarray(cross_r, np.int32)
+    integral = np.ascontiguousarray(integral, np.float32)
+    D, H, W = integral.shape
+    out = np.empty_like(integral)
+    (lib().oracle_cb_oii_hcross if horizontal else lib().oracle_cb_oii_vcross)(_i32(cross_l), _i32(cross_r), _f32(integral), W, H, D, _f32(out))
+    return out
+
+
+def cb_init_disparity(cost) -> np.ndarray:
+    cost = np.ascontiguousarray(cost, np.float32)
+    D, H, W = cost.shape
+    out = np.empty((H, W, 4), np.uint8)
+    lib().oracle_cb_init_disparity(_f32(cost), W, H, D, _u8(out))
+    return out
+
+
+def cb_disparity(init_rgba, cross, D: int = 61) -> np.ndarray:
+    init_rgba, cross = _img(init_rgba), np.ascontiguousarray(cross, np.int32)
+    H, W, _ = init_rgba.shape
+    out = np.empty_like(init_rgba)
+    lib().oracle_cb_disparity(_u8(init_rgba), _i32(cross), W, H, D, _u8(out))
+    return out
+
+
+def cross_full(left, right, D: int = 61, max_arm: int = 25, median_local: int = 3) -> dict:
+    """The whole cross-based method of main.cpp:258-367."""
+    left, right = _img(left), _img(right)
+    H, W, _ = left.shape
+    r = {k: np.empty((H, W, 4), np.uint8) for k in ("initial", "final", "median_l")}
+    rc = lib().oracle_cross_full(_u8(left), _u8(right), W, H, D, max_arm, median_local, _u8(r["initial"]), _u8(r["final"]), _u8(r["median_l"]))
+    if rc != 0:
+        raise RuntimeError(f"oracle_cross_full failed rc={rc}")
     return r

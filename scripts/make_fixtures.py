@@ -15,7 +15,8 @@ FILES = {
     "tsukuba": ["im1.png", "im5.png"], "teddy": ["im2.png", "im6.png"], "cones": ["im2.png", "im6.png"],
     "art": ["view1.png", "view5.png"], "laundry": ["view1.png", "view5.png"],
 }
-GOLDENS = ["asw_consistency_pre-reff.png", "asw_disparity.png", "asw_consistency_post-reff.png"]
+GOLDENS = ["asw_consistency_pre-reff.png", "asw_disparity.png", "asw_consistency_post-reff.png", "cross_based_initial.png",
+           "cross_based_disparity.png"]
 for ds, inputs in FILES.items():
     os.makedirs(os.path.join(OUT, ds), exist_ok=True)
     for f in inputs + GOLDENS:
