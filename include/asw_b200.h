@@ -209,6 +209,51 @@ ASW_API int asw_stereo(asw_ctx* ctx, const uint8_t* left_rgba, const uint8_t* ri
                        int refine_iters, uint8_t* disparity_rgba, uint8_t* consistency_pre_rgba, uint8_t* consistency_post_rgba,
                        asw_timing* timing, asw_tail_timing* tail_timing);
 
+/* ---- the reference's second method: cross-based matching on orthogonal integral images -------------
+ * (main.cpp:258-367; kernels cross.cl, aggregation.cl, integral_h.cl, oii_hcross.cl, integral_v.cl,
+ * oii_vcross.cl, init_disparity.cl, disparity.cl, median.cl).  Device pointers, reference layouts:
+ * cost volumes x + W*y + W*H*d; cross tables 4 planes of W*H ints (-h_minus, h_plus, -v_minus, v_plus). */
+typedef struct asw_cross_params {
+    int ndisp;          /* 61   (aggregation.cl:14, init_disparity.cl:11, disparity.cl:16; at most 256) */
+    int max_arm;        /* 25   (cross.cl:33-81) */
+    int median_local;   /* 3: the reference launches Median on local * floor(dim / local) work items (main.cpp:191-197),
+                           pixels beyond stay zero, as in its committed PNGs; 1 = filter the whole image */
+} asw_cross_params;
+
+/* the reference's log columns for this method (main.cpp:379-396), device times in ms */
+typedef struct asw_cross_timing {
+    float median_l_ms, median_r_ms, median_ms, cross_l_ms, cross_r_ms, cross_ms, aggregation_ms, integral_h_ms, oii_h_ms,
+        integral_v_ms, oii_v_ms, init_disparity_ms, final_disparity_ms, total_ms;
+} asw_cross_timing;
+
+ASW_API void asw_cross_params_default(asw_cross_params* p);
+/* Median as launched for this method: asw_Median, then the pixels outside local * floor(dim / local) zeroed */
+ASW_API int asw_Median_grid(asw_ctx* ctx, int W, int H, int local, const uint8_t* d_input_rgba, uint8_t* d_output_rgba);
+/* kernels/cross.cl:83-105 `Cross(input, output)`; args main.cpp:283-291 */
+ASW_API int asw_Cross(asw_ctx* ctx, int W, int H, const asw_cross_params* prm, const uint8_t* d_input_rgba, int* d_output);
+/* kernels/aggregation.cl:3-23 `Aggregation(input_l, input_r, output_cost)`; args main.cpp:295-298 */
+ASW_API int asw_Aggregation(asw_ctx* ctx, int W, int H, const asw_cross_params* prm, const uint8_t* d_input_l_rgba,
+                            const uint8_t* d_input_r_rgba, float* d_output_cost);
+/* kernels/integral_h.cl:3-17, integral_v.cl:3-17 `Integral_h/v(cost, size)`: in place; args main.cpp:304-305, 322-323 */
+ASW_API int asw_Integral_h(asw_ctx* ctx, int W, int H, const asw_cross_params* prm, float* d_cost);
+ASW_API int asw_Integral_v(asw_ctx* ctx, int W, int H, const asw_cross_params* prm, float* d_cost);
+/* kernels/oii_hcross.cl:1-31 `Oii_hcross(cross_l, cross_r, cost, temp_cost, size)`; args main.cpp:312-316 */
+ASW_API int asw_Oii_hcross(asw_ctx* ctx, int W, int H, const asw_cross_params* prm, const int* d_cross_l, const int* d_cross_r,
+                           const float* d_cost, float* d_temp_cost);
+/* kernels/oii_vcross.cl:1-32 `Oii_vcross(cross_l, cross_r, temp_cost, cost, size)`; args main.cpp:329-333 */
+ASW_API int asw_Oii_vcross(asw_ctx* ctx, int W, int H, const asw_cross_params* prm, const int* d_cross_l, const int* d_cross_r,
+                           const float* d_temp_cost, float* d_cost);
+/* kernels/init_disparity.cl:1-19 `Init_disparity(cost, output)`; args main.cpp:339-340 */
+ASW_API int asw_Init_disparity(asw_ctx* ctx, int W, int H, const asw_cross_params* prm, const float* d_cost, uint8_t* d_output_rgba);
+/* kernels/disparity.cl:1-41 `Disparity(input, input_cross, output)`; args main.cpp:346-348 */
+ASW_API int asw_Disparity(asw_ctx* ctx, int W, int H, const asw_cross_params* prm, const uint8_t* d_input_rgba, const int* d_input_cross,
+                          uint8_t* d_output_rgba);
+/* The whole method on host buffers (main.cpp:270-367).  Outputs (any may be NULL), each W*H*4: the reference's
+ * cross_based_initial.png, cross_based_disparity.png and median.png. */
+ASW_API int asw_cross_stereo(asw_ctx* ctx, const uint8_t* left_rgba, const uint8_t* right_rgba, int W, int H,
+                             const asw_cross_params* prm, uint8_t* initial_rgba, uint8_t* disparity_rgba, uint8_t* median_l_rgba,
+                             asw_cross_timing* timing);
+
 /* ---- device memory helpers (so a plain C/C++ host needs no CUDA headers) -------------
  * Replace clCreateBuffer / clCreateImage2D(COPY_HOST_PTR) / clEnqueueReadImage /
  * clReleaseMemObject, main.cpp:243-256,434-457,621-629,712-738. */

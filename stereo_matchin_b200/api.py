@@ -27,6 +27,8 @@ EXPORTS = [
     "asw_device_info", "asw_params_default", "asw_disparity", "asw_disparity_device", "asw_disparity_band_device",
     "asw_set_keep_volume", "asw_final_volume", "asw_Aggr", "asw_vSupport", "asw_hSupport", "asw_vCostAggregation",
     "asw_hCostAggregation", "asw_WTA", "asw_Constistency", "asw_ref_v", "asw_ref_h", "asw_WTA_REF", "asw_Median", "asw_stereo",
+    "asw_cross_params_default", "asw_Median_grid", "asw_Cross", "asw_Aggregation", "asw_Integral_h", "asw_Integral_v", "asw_Oii_hcross",
+    "asw_Oii_vcross", "asw_Init_disparity", "asw_Disparity", "asw_cross_stereo",
     "asw_dev_alloc", "asw_dev_free", "asw_memcpy_h2d", "asw_memcpy_d2h",
     "asw_host_alloc", "asw_host_free", "asw_set_kernel_family",
 ]
@@ -59,6 +61,30 @@ class CTailTiming(C.Structure):
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class CCrossParams(C.Structure):
+    _fields_ = [("ndisp", C.c_int), ("max_arm", C.c_int), ("median_local", C.c_int)]
+
+
+class CCrossTiming(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("median_l_ms", "median_r_ms", "median_ms", "cross_l_ms", "cross_r_ms", "cross_ms", "aggregation_ms",
+                                          "integral_h_ms", "oii_h_ms", "integral_v_ms", "oii_v_ms", "init_disparity_ms",
+                                          "final_disparity_ms", "total_ms")]
+
+    def as_dict(self) -> dict:
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+@dataclass
+class CrossParams:
+    """Defaults = the reference's literals (aggregation.cl:14, cross.cl:33-81, main.cpp:191-197)."""
+    ndisp: int = 61
+    max_arm: int = 25
+    median_local: int = 3
+
+    def c(self) -> CCrossParams:
+        return CCrossParams(self.ndisp, self.max_arm, self.median_local)
 
 
 @dataclass
@@ -119,6 +145,19 @@ def load_library() -> C.CDLL:
     lib.asw_WTA_REF.argtypes = [vp, C.c_int, C.c_int, pp, f32p, f32p, f32p, u8p, u8p, f32p, f32p, f32p, f32p]
     lib.asw_Median.argtypes = [vp, C.c_int, C.c_int, u8p, u8p]
     lib.asw_stereo.argtypes = [vp, u8p, u8p, C.c_int, C.c_int, pp, C.c_int, u8p, u8p, u8p, tp, C.POINTER(CTailTiming)]
+    cp = C.POINTER(CCrossParams)
+    lib.asw_cross_params_default.argtypes = [cp]
+    lib.asw_cross_params_default.restype = None
+    lib.asw_Median_grid.argtypes = [vp, C.c_int, C.c_int, C.c_int, u8p, u8p]
+    lib.asw_Cross.argtypes = [vp, C.c_int, C.c_int, cp, u8p, vp]
+    lib.asw_Aggregation.argtypes = [vp, C.c_int, C.c_int, cp, u8p, u8p, f32p]
+    lib.asw_Integral_h.argtypes = [vp, C.c_int, C.c_int, cp, f32p]
+    lib.asw_Integral_v.argtypes = [vp, C.c_int, C.c_int, cp, f32p]
+    lib.asw_Oii_hcross.argtypes = [vp, C.c_int, C.c_int, cp, vp, vp, f32p, f32p]
+    lib.asw_Oii_vcross.argtypes = [vp, C.c_int, C.c_int, cp, vp, vp, f32p, f32p]
+    lib.asw_Init_disparity.argtypes = [vp, C.c_int, C.c_int, cp, f32p, u8p]
+    lib.asw_Disparity.argtypes = [vp, C.c_int, C.c_int, cp, u8p, vp, u8p]
+    lib.asw_cross_stereo.argtypes = [vp, u8p, u8p, C.c_int, C.c_int, cp, u8p, u8p, u8p, C.POINTER(CCrossTiming)]
     lib.asw_dev_alloc.argtypes = [vp, C.POINTER(vp), C.c_size_t]
     lib.asw_dev_free.argtypes = [vp, vp]
     lib.asw_memcpy_h2d.argtypes = [vp, vp, vp, C.c_size_t]
@@ -292,6 +331,26 @@ class AswContext:
         out["timing"] = tm.as_dict()
         out["tail_timing"] = tt.as_dict()
         return out
+
+    def cross_stereo(self, left: np.ndarray, right: np.ndarray, params: "CrossParams | None" = None) -> dict:
+        """The whole cross-based method (asw_cross_stereo): initial and final disparity images + the median of the left image."""
+        params = params or CrossParams()
+        left, right = _rgba(left), _rgba(right)
+        H, W, _ = left.shape
+        out = {k: np.empty((H, W, 4), np.uint8) for k in ("initial", "final", "median_l")}
+        tm, p = CCrossTiming(), params.c()
+        self._check(self.lib.asw_cross_stereo(self.h, left.ctypes.data, right.ctypes.data, W, H, C.byref(p), out["initial"].ctypes.data,
+                                              out["final"].ctypes.data, out["median_l"].ctypes.data, C.byref(tm)))
+        out["timing"] = tm.as_dict()
+        return out
+
+    def cb_op(self, name: str, W: int, H: int, params: "CrossParams", *ptrs):
+        """Per-operator entry points of the cross-based method: asw_Cross, asw_Aggregation, asw_Integral_h, ..."""
+        p = params.c()
+        self._check(getattr(self.lib, name)(self.h, W, H, C.byref(p), *ptrs))
+
+    def asw_Median_grid(self, W, H, local, input_, output):
+        self._check(self.lib.asw_Median_grid(self.h, W, H, local, input_, output))
 
     def asw_Constistency(self, W, H, params, ref, tar, confidence_ref, confidence_tar, output, output_red):
         p = params.c()

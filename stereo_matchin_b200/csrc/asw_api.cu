@@ -16,6 +16,7 @@
 #include "asw_kernels_tiled.cuh"
 #include "asw_kernels_tma.cuh"
 #include "asw_kernels_tail.cuh"
+#include "asw_kernels_cross.cuh"
 
 using namespace asw;
 
@@ -46,6 +47,7 @@ struct asw_ctx {
     Scratch vol_ref;                       // final volume in the reference layout (keep_volume)
     Scratch fimg_l, fimg_r;                // images as float4 (r, g, b, 0), sampler conversion applied
     Scratch tail[12];                      // whole-method buffers (asw_stereo)
+    Scratch cb[10];                        // cross-based method buffers (asw_cross_stereo)
     enum { kMaxEvents = 96 };
     cudaEvent_t ev[kMaxEvents] = {};
 };
@@ -382,6 +384,7 @@ int asw_destroy(asw_ctx* ctx) {
                       &ctx->hR, &ctx->vol[0], &ctx->vol[1], &ctx->vol[2], &ctx->den_v, &ctx->den_h, &ctx->vol_ref, &ctx->fimg_l, &ctx->fimg_r};
     for (Scratch* s : all) if (s->p) cudaFree(s->p);
     for (Scratch& s : ctx->tail) if (s.p) cudaFree(s.p);
+    for (Scratch& s : ctx->cb) if (s.p) cudaFree(s.p);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -648,6 +651,158 @@ int asw_stereo(asw_ctx* ctx, const uint8_t* left, const uint8_t* right, int W, i
             tail->median_ms = et.ms(e_ref, e_med);
             tail->total_ms = hot.total_ms + et.ms(e0, e_med);
         }
+    }
+    return ASW_OK;
+}
+
+// ---- the cross-based method (main.cpp:258-367) ---------------------------------------------------
+void asw_cross_params_default(asw_cross_params* p) {
+    if (!p) return;
+    p->ndisp = 61;
+    p->max_arm = 25;
+    p->median_local = 3;
+}
+
+namespace {
+int check_cross(asw_ctx* ctx, int W, int H, const asw_cross_params* p) {
+    if (!ctx) return ASW_ERR_INVALID;
+    if (!p) return fail(ctx, ASW_ERR_INVALID, "params is NULL");
+    if (W <= 0 || H <= 0) return fail(ctx, ASW_ERR_INVALID, "W and H must be positive");
+    if (p->ndisp <= 0 || p->max_arm < 1 || p->median_local < 1) return fail(ctx, ASW_ERR_INVALID, "ndisp > 0, max_arm >= 1, median_local >= 1 required");
+    if (p->ndisp > 256 || H > 65535) return fail(ctx, ASW_ERR_UNSUPPORTED, "ndisp is limited to 256 (8-bit disparity images), H to 65535");
+    return ASW_OK;
+}
+#define CB_PROLOGUE(ptr_ok)                                                        \
+    int st = check_cross(ctx, W, H, prm);                                          \
+    if (st) return st;                                                             \
+    if (!(ptr_ok)) return fail(ctx, ASW_ERR_INVALID, "device pointer is NULL");    \
+    CU(cudaSetDevice(ctx->device));
+#define CB_EPILOGUE     \
+    ctx->launches++;    \
+    CU(cudaGetLastError()); \
+    return ASW_OK;
+}  // namespace
+
+int asw_Median_grid(asw_ctx* ctx, int W, int H, int local, const uint8_t* in, uint8_t* out) {
+    int st = asw_Median(ctx, W, H, in, out);
+    if (st) return st;
+    if (local < 1) return fail(ctx, ASW_ERR_INVALID, "local must be >= 1");
+    const int We = local * (W / local), He = local * (H / local);
+    if (We < W || He < H) {
+        k_cb_zero_border<<<dim3((W + 127) / 128, H), 128, 0, ctx->stream>>>((uint32_t*)out, W, H, We, He);
+        ctx->launches++;
+        CU(cudaGetLastError());
+    }
+    return ASW_OK;
+}
+
+int asw_Cross(asw_ctx* ctx, int W, int H, const asw_cross_params* prm, const uint8_t* in, int* out) {
+    CB_PROLOGUE(in && out)
+    k_cb_cross<<<dim3((W + 127) / 128, H), 128, 0, ctx->stream>>>((const uint32_t*)in, W, H, prm->max_arm, out);
+    CB_EPILOGUE
+}
+
+int asw_Aggregation(asw_ctx* ctx, int W, int H, const asw_cross_params* prm, const uint8_t* l, const uint8_t* r, float* cost) {
+    CB_PROLOGUE(l && r && cost)
+    k_cb_aggregation<<<dim3((W + 127) / 128, H, prm->ndisp), 128, 0, ctx->stream>>>((const uint32_t*)l, (const uint32_t*)r, W, H, cost);
+    CB_EPILOGUE
+}
+
+int asw_Integral_h(asw_ctx* ctx, int W, int H, const asw_cross_params* prm, float* cost) {
+    CB_PROLOGUE(cost)
+    const int nrows = H * prm->ndisp;
+    k_cb_integral_h<<<(nrows + 31) / 32, dim3(32, 8), 0, ctx->stream>>>(cost, W, nrows);
+    CB_EPILOGUE
+}
+
+int asw_Integral_v(asw_ctx* ctx, int W, int H, const asw_cross_params* prm, float* cost) {
+    CB_PROLOGUE(cost)
+    k_cb_integral_v<<<dim3((W + 63) / 64, prm->ndisp), 64, 0, ctx->stream>>>(cost, W, H);
+    CB_EPILOGUE
+}
+
+int asw_Oii_hcross(asw_ctx* ctx, int W, int H, const asw_cross_params* prm, const int* cl, const int* cr, const float* cost, float* tmp) {
+    CB_PROLOGUE(cl && cr && cost && tmp)
+    k_cb_oii<true><<<dim3((W + 127) / 128, H, prm->ndisp), 128, 0, ctx->stream>>>(cl, cr, cost, W, H, tmp);
+    CB_EPILOGUE
+}
+
+int asw_Oii_vcross(asw_ctx* ctx, int W, int H, const asw_cross_params* prm, const int* cl, const int* cr, const float* tmp, float* cost) {
+    CB_PROLOGUE(cl && cr && cost && tmp)
+    k_cb_oii<false><<<dim3((W + 127) / 128, H, prm->ndisp), 128, 0, ctx->stream>>>(cl, cr, tmp, W, H, cost);
+    CB_EPILOGUE
+}
+
+int asw_Init_disparity(asw_ctx* ctx, int W, int H, const asw_cross_params* prm, const float* cost, uint8_t* out) {
+    CB_PROLOGUE(cost && out)
+    k_cb_init_disparity<<<dim3((W + 127) / 128, H), 128, 0, ctx->stream>>>(cost, W, H, prm->ndisp, (uint32_t*)out);
+    CB_EPILOGUE
+}
+
+int asw_Disparity(asw_ctx* ctx, int W, int H, const asw_cross_params* prm, const uint8_t* in, const int* cross, uint8_t* out) {
+    CB_PROLOGUE(in && cross && out)
+    k_cb_disparity<256><<<dim3((W + 7) / 8, H), dim3(32, 8), 0, ctx->stream>>>((const uint32_t*)in, cross, W, H, prm->ndisp, (uint32_t*)out);
+    CB_EPILOGUE
+}
+
+int asw_cross_stereo(asw_ctx* ctx, const uint8_t* left, const uint8_t* right, int W, int H, const asw_cross_params* prm, uint8_t* initial,
+                     uint8_t* disparity, uint8_t* median_l, asw_cross_timing* tm) {
+    int st = check_cross(ctx, W, H, prm);
+    if (st) return st;
+    if (!left || !right) return fail(ctx, ASW_ERR_INVALID, "image pointer is NULL");
+    CU(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)W * H, vol = sizeof(float) * n * prm->ndisp;
+    // 0 left 1 right 2 median_l 3 median_r 4 cross_l 5 cross_r 6 cost 7 temp_cost 8 disparity + f_disparity 9 cross_method
+    const size_t sz[10] = {n * 4, n * 4, n * 4, n * 4, n * 16, n * 16, vol, vol, n * 8, n * 4};
+    for (int i = 0; i < 10; i++)
+        if ((st = ensure(ctx, ctx->cb[i], sz[i]))) return st;
+    uint8_t *dl = (uint8_t*)ctx->cb[0].p, *dr = (uint8_t*)ctx->cb[1].p, *ml = (uint8_t*)ctx->cb[2].p, *mr = (uint8_t*)ctx->cb[3].p;
+    int *cl = (int*)ctx->cb[4].p, *cr = (int*)ctx->cb[5].p;
+    float *cost = (float*)ctx->cb[6].p, *tmp = (float*)ctx->cb[7].p;
+    uint8_t *disp = (uint8_t*)ctx->cb[8].p, *fdisp = disp + n * 4, *fin = (uint8_t*)ctx->cb[9].p;
+    ctx->launches = 0;
+    CU(cudaMemcpyAsync(dl, left, n * 4, cudaMemcpyHostToDevice, ctx->stream));                 // main.cpp:243-244
+    CU(cudaMemcpyAsync(dr, right, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    EvTimer et{ctx, tm != nullptr};
+    const int e0 = et.mark();
+    if ((st = asw_Median_grid(ctx, W, H, prm->median_local, dl, ml))) return st;               // :270-274
+    const int e1 = et.mark();
+    if ((st = asw_Median_grid(ctx, W, H, prm->median_local, dr, mr))) return st;               // :276-279
+    const int e2 = et.mark();
+    if ((st = asw_Cross(ctx, W, H, prm, ml, cl))) return st;                                   // :283-286
+    const int e3 = et.mark();
+    if ((st = asw_Cross(ctx, W, H, prm, mr, cr))) return st;                                   // :288-291
+    const int e4 = et.mark();
+    if ((st = asw_Aggregation(ctx, W, H, prm, ml, mr, cost))) return st;                       // :295-299
+    const int e5 = et.mark();
+    if ((st = asw_Integral_h(ctx, W, H, prm, cost))) return st;                                // :304-307
+    const int e6 = et.mark();
+    if ((st = asw_Oii_hcross(ctx, W, H, prm, cl, cr, cost, tmp))) return st;                   // :312-318
+    const int e7 = et.mark();
+    if ((st = asw_Integral_v(ctx, W, H, prm, tmp))) return st;                                 // :322-325
+    const int e8 = et.mark();
+    if ((st = asw_Oii_vcross(ctx, W, H, prm, cl, cr, tmp, cost))) return st;                   // :329-335
+    const int e9 = et.mark();
+    if ((st = asw_Init_disparity(ctx, W, H, prm, cost, disp))) return st;                      // :339-342
+    const int e10 = et.mark();
+    if ((st = asw_Disparity(ctx, W, H, prm, disp, cl, fdisp))) return st;                      // :346-350
+    const int e11 = et.mark();
+    if ((st = asw_Median_grid(ctx, W, H, prm->median_local, fdisp, fin))) return st;           // :352-354
+    const int e12 = et.mark();
+    if (initial) CU(cudaMemcpyAsync(initial, disp, n * 4, cudaMemcpyDeviceToHost, ctx->stream));     // :357-359
+    if (disparity) CU(cudaMemcpyAsync(disparity, fin, n * 4, cudaMemcpyDeviceToHost, ctx->stream));  // :361-363
+    if (median_l) CU(cudaMemcpyAsync(median_l, ml, n * 4, cudaMemcpyDeviceToHost, ctx->stream));     // :365-367
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (tm) {
+        memset(tm, 0, sizeof *tm);
+        tm->median_l_ms = et.ms(e0, e1);  tm->median_r_ms = et.ms(e1, e2);  tm->median_ms = et.ms(e0, e2);
+        tm->cross_l_ms = et.ms(e2, e3);   tm->cross_r_ms = et.ms(e3, e4);   tm->cross_ms = et.ms(e2, e4);
+        tm->aggregation_ms = et.ms(e4, e5);
+        tm->integral_h_ms = et.ms(e5, e6);  tm->oii_h_ms = et.ms(e6, e7);
+        tm->integral_v_ms = et.ms(e7, e8);  tm->oii_v_ms = et.ms(e8, e9);
+        tm->init_disparity_ms = et.ms(e9, e10);
+        tm->final_disparity_ms = et.ms(e10, e11);
+        tm->total_ms = et.ms(e0, e12);
     }
     return ASW_OK;
 }
