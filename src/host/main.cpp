@@ -10,17 +10,21 @@
 // sequence (main.cpp:119-130,158-172,210-256,434-526) -> asw_create + asw_disparity.
 // --method hot (default) runs the hot path only and writes asw_disparity<suffix>.png = the WTA image;
 // --method whole runs the whole ASW method (asw_stereo: + consistency, k refinement rounds, median,
-// main.cpp:529-631) and writes the reference's three ASW PNGs (main.cpp:621-631) with the suffix.
-// Out of scope (columns written as 0): the cross-based method.
+// main.cpp:529-631) and writes the reference's three ASW PNGs (main.cpp:621-631) with the suffix;
+// --method cross runs the cross-based method (asw_cross_stereo, main.cpp:258-367) and writes
+// cross_based_initial / cross_based_disparity / median<suffix>.png (main.cpp:357-367);
+// --method both = cross + whole, the reference's full per-run sequence.  Columns of a method that did
+// not run are written as 0.
 //
 // Usage: stereo_matching [--pics pics.txt] [--root DIR] [--runs 10] [--device 0] [--ndisp 61]
-//                        [--iterations 7] [--method hot|whole] [--refine 6] [--out-suffix _wta] [--log FILE]
+//                        [--iterations 7] [--method hot|whole|cross|both] [--refine 6] [--out-suffix _wta] [--log FILE]
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "asw_b200.h"
@@ -40,7 +44,7 @@ static const char* kHeader =
 int main(int argc, char** argv) {
     std::string pics = "pics.txt", root = ".", suffix = "_wta", log_name;
     int runs = 10, device = 0, refine = 6;   // k = 6, main.cpp:176
-    bool whole = false;
+    bool whole = false, hot = true, cross = false;
     asw_params prm;
     asw_params_default(&prm);
     for (int i = 1; i < argc; i++) {
@@ -58,8 +62,10 @@ int main(int argc, char** argv) {
         else if (a == "--refine") refine = atoi(next("--refine"));
         else if (a == "--method") {
             std::string m = next("--method");
-            if (m != "hot" && m != "whole") { fprintf(stderr, "--method must be hot or whole\n"); return 2; }
-            whole = m == "whole";
+            if (m != "hot" && m != "whole" && m != "cross" && m != "both") { fprintf(stderr, "--method must be hot, whole, cross or both\n"); return 2; }
+            whole = m == "whole" || m == "both";
+            cross = m == "cross" || m == "both";
+            hot = m == "hot";
         }
         else if (a == "--out-suffix") suffix = next("--out-suffix");
         else if (a == "--log") log_name = next("--log");
@@ -115,8 +121,31 @@ int main(int argc, char** argv) {
             printf("\n---Working...\nRaw cost aggregation..  \ngestalt principle - support area.. \nCost aggregation.. \nWTA.. ");
             asw_timing t;
             asw_tail_timing tt;
+            asw_cross_timing ct;
+            memset(&t, 0, sizeof t);
             memset(&tt, 0, sizeof tt);
-            if (whole)
+            memset(&ct, 0, sizeof ct);
+            if (cross) {                                                             // main.cpp:258-367
+                std::vector<unsigned char> ini(disp.size()), fin(disp.size()), med(disp.size());
+                asw_cross_params cprm;
+                asw_cross_params_default(&cprm);
+                cprm.ndisp = prm.ndisp;
+                st = asw_cross_stereo(ctx, imgL.pixel.data(), imgR.pixel.data(), (int)W, (int)H, &cprm, ini.data(), fin.data(), med.data(), &ct);
+                if (st != ASW_OK) {
+                    printf("error executing the cross-based method: %d (%s)\n", st, asw_last_error(ctx));
+                    rc = 1;
+                } else if (run == 0) {
+                    const std::string dir = root + "/" + folder_name[img] + "/";
+                    const std::pair<const char*, const std::vector<unsigned char>*> outs[3] = {
+                        {"cross_based_initial", &ini}, {"cross_based_disparity", &fin}, {"median", &med}};
+                    for (const auto& o : outs) {
+                        unsigned e = png_io::encode(dir + o.first + suffix + ".png", *o.second, W, H);
+                        if (e) { fprintf(stderr, "cannot write %s%s%s.png: %s\n", dir.c_str(), o.first, suffix.c_str(), png_io::error_text(e)); rc = 1; }
+                    }
+                }
+            }
+            if (!whole && !hot) st = ASW_OK;
+            else if (whole)
                 st = asw_stereo(ctx, imgL.pixel.data(), imgR.pixel.data(), (int)W, (int)H, &prm, refine, disp.data(), pre.data(), post.data(), &t, &tt);
             else
                 st = asw_disparity(ctx, imgL.pixel.data(), imgR.pixel.data(), (int)W, (int)H, &prm, disp.data(), nullptr, nullptr, &t);
@@ -125,7 +154,7 @@ int main(int argc, char** argv) {
                 rc = 1;
                 continue;
             }
-            if (run == 0) {   // the reference's PNGs on disk come from run 1
+            if (run == 0 && (whole || hot)) {   // the reference's PNGs on disk come from run 1
                 const std::string dir = root + "/" + folder_name[img] + "/";
                 auto save = [&](const std::string& name, const std::vector<unsigned char>& px) {
                     unsigned e = png_io::encode(dir + name + suffix + ".png", px, W, H);
@@ -137,7 +166,11 @@ int main(int argc, char** argv) {
                     save("asw_consistency_post-reff", post);                    // main.cpp:629-631
                 }
             }
-            for (int c = 0; c < 14; c++) fprintf(to_file, "%0.3f\t", 0.0);   // cross-based columns: out of scope
+            // medL_solo medR_solo med_full cross_h cross_v cross_full aggregation integral_h aggr_h integral_v aggr_v
+            // init_disp final_disp "cross method total" (main.cpp:379-396)
+            fprintf(to_file, "%0.3f\t%0.3f\t%0.3f\t%0.3f\t%0.3f\t%0.3f\t%0.3f\t%0.3f\t%0.3f\t%0.3f\t%0.3f\t%0.3f\t%0.3f\t%0.3f\t", ct.median_l_ms,
+                    ct.median_r_ms, ct.median_ms, ct.cross_l_ms, ct.cross_r_ms, ct.cross_ms, ct.aggregation_ms, ct.integral_h_ms, ct.oii_h_ms,
+                    ct.integral_v_ms, ct.oii_v_ms, ct.init_disparity_ms, ct.final_disparity_ms, ct.total_ms);
             fprintf(to_file, "\t\t");
             fprintf(to_file, "%0.3f\t%0.3f\t%0.3f\t%0.3f\t%0.3f\t%0.3f\t", t.raw_ms, t.supp_ms, t.vagg_mean_ms, t.hagg_mean_ms,
                     t.agg_total_ms, t.wta_ms);
@@ -146,7 +179,7 @@ int main(int argc, char** argv) {
             fprintf(to_file, "%0.3f\t%0.3f\t%0.3f\t%0.3f\t%0.3f\t%0.3f\t%0.3f\t%0.3f\t%0.3f\t", tt.right_wta_ms + tt.consistency_ms,
                     tt.vref_mean_l_ms, tt.vref_mean_r_ms, tt.href_mean_l_ms, tt.href_mean_r_ms, tt.wta_ref_mean_ms, tt.consistency_mean_ms,
                     tt.refinement_total_ms, tt.median_ms);
-            const float whole_ms = whole ? tt.total_ms : t.total_ms;
+            const float whole_ms = whole ? tt.total_ms : hot ? t.total_ms : ct.total_ms;
             fprintf(to_file, "%0.3f\t", whole_ms);
             sum_total += whole_ms;
         }

@@ -100,3 +100,26 @@ def test_cross_error_behaviour(ctx):
         ctx.cross_stereo(L, R, CP(ndisp=300))
     with pytest.raises(AswError):
         ctx.cross_stereo(L, R, CP(max_arm=0))
+
+
+def test_host_binary_both_methods(tmp_path):
+    """The pics.txt-driven host program runs the reference's full per-run sequence (cross-based + ASW)."""
+    import shutil
+    import subprocess
+    from conftest import PAIRS
+    exe = os.path.join(os.path.dirname(GOLDEN), "..", "src", "host", "stereo_matching")
+    assert os.path.exists(exe), "run `python -m stereo_matchin_b200.build` first"
+    os.makedirs(tmp_path / "teddy")
+    for f in PAIRS["teddy"]:
+        shutil.copy(os.path.join(GOLDEN, "teddy", f), tmp_path / "teddy" / f)
+    (tmp_path / "pics.txt").write_text("teddy/im2.png\nteddy/im6.png\n")
+    r = subprocess.run([exe, "--pics", str(tmp_path / "pics.txt"), "--root", str(tmp_path), "--runs", "1", "--method", "both",
+                        "--out-suffix", "", "--log", str(tmp_path / "log.tsv")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert np.array_equal(load_rgba(str(tmp_path / "teddy" / "cross_based_disparity.png")),
+                          load_rgba(os.path.join(GOLDEN, "teddy", "cross_based_disparity.png")))
+    for name in ("cross_based_initial.png", "median.png", "asw_disparity.png", "asw_consistency_pre-reff.png", "asw_consistency_post-reff.png"):
+        assert os.path.exists(tmp_path / "teddy" / name), name
+    run1 = [ln for ln in (tmp_path / "log.tsv").read_text().splitlines() if ln.startswith("Run 1")][0].split("\t")
+    vals = [float(v) for v in run1[1:] if v.strip()]
+    assert len(vals) == 30 and all(v > 0 for v in vals)      # every column of the reference's log is filled
