@@ -87,6 +87,13 @@ def oracle_sample(L, R, D, r, rows):
     """Times the CPU oracle on the top `rows` rows of the workload (bounded sample)."""
     from oracle import asw_oracle as O
     O.lib()
+    # all host threads this process may use: torchrun exports OMP_NUM_THREADS=1 to its workers, which would
+    # otherwise turn the 16-core baseline into a single-threaded one
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncpu = os.cpu_count() or 1
+    O.set_num_threads(ncpu)
     rows = min(rows, L.shape[0])
     Ls, Rs = np.ascontiguousarray(L[:rows]), np.ascontiguousarray(R[:rows])
     p = O.OracleParams(ndisp=D, iterations=r)
