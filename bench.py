@@ -291,7 +291,7 @@ def main():
         achieved = pass_flops / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
         peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
         hbm_peak = json.load(open(peaks_file)).get("hbm_gbs") if os.path.exists(peaks_file) else 6650.0
-        Dp = (D + 127) // 128 * 128 if args.family == 0 else (D + 31) // 32 * 32
+        Dp = (D + 63) // 64 * 64 if args.family == 0 else (D + 31) // 32 * 32
         pass_bytes = 3.0 * 4 * W * rows_mean * Dp      # tiled kernels: read cost + read denominator + write cost
         traffic, traffic_src = None, None                       # DRAM bytes per launch of that kernel, from the committed ncu --set full capture
         tfiles = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_traffic.json")) if os.path.isdir(os.path.join(ROOT, "profiles")) else []

@@ -266,7 +266,7 @@ ASW_API int asw_host_alloc(asw_ctx* ctx, void** h_ptr, size_t bytes);
 ASW_API int asw_host_free(asw_ctx* ctx, void* h_ptr);
 
 /* Selects the kernel family of the fused path: 0 = automatic (default: the TMA-fed sm_100a kernels for
- * radius 16, ndisp padded to a multiple of 128 internally), 1 = the straightforward one-thread-per-output
+ * radius 16, ndisp padded to a multiple of 64 internally), 1 = the straightforward one-thread-per-output
  * kernels of the per-operator entry points, 2 = the earlier tiled kernels without TMA (1 and 2 are kept as
  * on-device cross-checks).  All are CUDA; none is a CPU path. */
 ASW_API int asw_set_kernel_family(asw_ctx* ctx, int family);
