@@ -216,7 +216,9 @@ int run_band(asw_ctx* ctx, const uint8_t* dl, const uint8_t* dr, int W, int H, i
         return st;
     for (int i = 0; i < ((tiled || tma) ? 2 : 3); i++)
         if ((st = ensure(ctx, ctx->vol[i], vol_bytes))) return st;
-    if ((tiled || tma) && r > 0 && ((st = ensure(ctx, ctx->den_v, vol_bytes)) || (st = ensure(ctx, ctx->den_h, vol_bytes)))) return st;
+    // the TMA family keeps the vertical denominators in a private per-thread layout (vden_* in asw_kernels_tma.cuh)
+    const size_t denv_bytes = tma ? sizeof(float) * vden_total_floats(W, b.y_off, b.Hb, Dp) : vol_bytes;
+    if ((tiled || tma) && r > 0 && ((st = ensure(ctx, ctx->den_v, denv_bytes)) || (st = ensure(ctx, ctx->den_h, vol_bytes)))) return st;
     float *vL = (float*)ctx->vL.p, *hL = (float*)ctx->hL.p, *vR = (float*)ctx->vR.p, *hR = (float*)ctx->hR.p;
 
     ctx->launches = 0;
