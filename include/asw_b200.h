@@ -137,6 +137,19 @@ ASW_API int asw_disparity_band_device(asw_ctx* ctx, const uint8_t* d_left_rgba, 
                                       int y0, int y1, const asw_params* prm, uint8_t* d_disp_rgba, uint8_t* d_disp_d,
                                       float* d_conf, asw_timing* timing);
 
+/* Disparity-shard variant for multi-GPU sharding without halo work: aggregates only the disparities [d0, d1)
+ * (d0 a multiple of 64) for output rows [y0, y1) and returns the shard's partial winner-take-all result per pixel:
+ * smallest and second smallest aggregated cost and the GLOBAL index of the smallest ((y1-y0)*W each).  Planes of the
+ * cost volume never interact during aggregation (asw_vcost_aggregation.cl / asw_hcost_aggregation.cl: d is a pure
+ * index), so shards are independent; asw_merge_shards combines them.  Needs the default kernel family, radius 16. */
+ASW_API int asw_disparity_shard_device(asw_ctx* ctx, const uint8_t* d_left_rgba, const uint8_t* d_right_rgba, int W, int H,
+                                       int y0, int y1, int d0, int d1, const asw_params* prm, float* d_min1, float* d_min2,
+                                       int* d_arg, asw_timing* timing);
+/* Combines `nshards` partial results ([shard][rows][W] arrays, shards in ascending disparity order, e.g. straight
+ * out of an all-gather) into the outputs of asw_WTA; bit-identical to the unsharded call.  Any output may be NULL. */
+ASW_API int asw_merge_shards(asw_ctx* ctx, int W, int rows, int ndisp, int nshards, const float* d_min1, const float* d_min2,
+                             const int* d_arg, uint8_t* d_disp_rgba, uint8_t* d_disp_d, float* d_conf);
+
 /* Keep the final aggregated volume of the last asw_disparity* call (device pointer, layout
  * above, rows of the processed band) for consumers such as the right-view WTA / consistency
  * check.  Returns NULL if the last call did not materialise it.  Enable with

@@ -24,7 +24,7 @@ ASW_OK, ASW_ERR_INVALID, ASW_ERR_CUDA, ASW_ERR_NOMEM, ASW_ERR_UNSUPPORTED = rang
 # every symbol include/asw_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
     "asw_version", "asw_strerror", "asw_create", "asw_destroy", "asw_last_error", "asw_stream", "asw_sync",
-    "asw_device_info", "asw_params_default", "asw_disparity", "asw_disparity_device", "asw_disparity_band_device",
+    "asw_device_info", "asw_params_default", "asw_disparity", "asw_disparity_device", "asw_disparity_band_device", "asw_disparity_shard_device", "asw_merge_shards",
     "asw_set_keep_volume", "asw_final_volume", "asw_Aggr", "asw_vSupport", "asw_hSupport", "asw_vCostAggregation",
     "asw_hCostAggregation", "asw_WTA", "asw_Constistency", "asw_ref_v", "asw_ref_h", "asw_WTA_REF", "asw_Median", "asw_stereo",
     "asw_cross_params_default", "asw_Median_grid", "asw_Cross", "asw_Aggregation", "asw_Integral_h", "asw_Integral_v", "asw_Oii_hcross",
@@ -130,6 +130,8 @@ def load_library() -> C.CDLL:
     lib.asw_disparity.argtypes = [vp, u8p, u8p, C.c_int, C.c_int, pp, u8p, u8p, f32p, tp]
     lib.asw_disparity_device.argtypes = [vp, u8p, u8p, C.c_int, C.c_int, pp, u8p, u8p, f32p, tp]
     lib.asw_disparity_band_device.argtypes = [vp, u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, pp, u8p, u8p, f32p, tp]
+    lib.asw_disparity_shard_device.argtypes = [vp, u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, pp, f32p, f32p, vp, tp]
+    lib.asw_merge_shards.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, f32p, f32p, vp, u8p, u8p, f32p]
     lib.asw_set_keep_volume.argtypes = [vp, C.c_int]
     lib.asw_final_volume.restype = vp
     lib.asw_final_volume.argtypes = [vp]
@@ -372,6 +374,17 @@ class AswContext:
 
     def asw_Median(self, W, H, input_, output):
         self._check(self.lib.asw_Median(self.h, W, H, input_, output))
+
+    def disparity_shard_raw(self, left_ptr, right_ptr, W, H, params, band, dshard, min1_ptr, min2_ptr, arg_ptr, timing=False):
+        """asw_disparity_shard_device: rows band = (y0, y1), disparities dshard = (d0, d1); partial WTA triples out."""
+        tm = CTiming() if timing else None
+        p = params.c()
+        self._check(self.lib.asw_disparity_shard_device(self.h, left_ptr, right_ptr, W, H, band[0], band[1], dshard[0], dshard[1], C.byref(p),
+                                                        min1_ptr, min2_ptr, arg_ptr, C.byref(tm) if tm is not None else None))
+        return tm.as_dict() if tm is not None else None
+
+    def merge_shards(self, W, rows, ndisp, nshards, min1_ptr, min2_ptr, arg_ptr, rgba_ptr, d_ptr, conf_ptr):
+        self._check(self.lib.asw_merge_shards(self.h, W, rows, ndisp, nshards, min1_ptr, min2_ptr, arg_ptr, rgba_ptr, d_ptr, conf_ptr))
 
     def final_volume_ptr(self) -> int:
         return int(self.lib.asw_final_volume(self.h) or 0)

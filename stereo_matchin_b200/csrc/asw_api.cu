@@ -193,15 +193,24 @@ struct StageTimes {
     } while (0)
 
 // The hot path on device buffers for output rows [y0, y1) of a W x H frame (main.cpp:463-526).
+struct Shard {            // disparity shard [d0, d1) of the problem and where its partial WTA result goes (TMA family only)
+    int d0 = 0, d1 = -1;
+    float *min1 = nullptr, *min2 = nullptr;
+    int* arg = nullptr;
+};
+
 int run_band(asw_ctx* ctx, const uint8_t* dl, const uint8_t* dr, int W, int H, int y0, int y1, const asw_params* p,
-             uint8_t* d_rgba, uint8_t* d_d, float* d_conf, asw_timing* tm) {
-    const int R = p->radius, T = 2 * R + 1, D = p->ndisp, r = p->iterations;
+             uint8_t* d_rgba, uint8_t* d_d, float* d_conf, asw_timing* tm, const Shard* sh = nullptr) {
+    const int R = p->radius, T = 2 * R + 1, Dfull = p->ndisp, r = p->iterations;
+    const int sd0 = sh ? sh->d0 : 0, sd1 = sh ? sh->d1 : Dfull;
+    const int D = sd1 - sd0;                                   // disparities aggregated by this call
     // rows whose values can influence rows [y0,y1): R rows per V pass (H passes stay in-row)
     const int ya = max(0, y0 - r * R), yb = min(H, y1 + r * R);
     Band b{W, H, ya, yb - ya};
-    const bool tma = ctx->family == 0 && tma_supported(R, D);
+    const bool tma = ctx->family == 0 && tma_supported(R, Dfull);
+    if (sh && !tma) return fail(ctx, ASW_ERR_UNSUPPORTED, "disparity shards need the TMA kernel family (radius 16, family 0)");
     const bool tiled = !tma && (ctx->family == 0 || ctx->family == 2) && tiled_supported(R);
-    const TL tl = make_tl(b, D);
+    const TL tl = make_tl(b, Dfull, sd0, sd1);
     const int Dp = tma ? tma_padded_D(D) : tiled ? padded_D(D) : D;
     const size_t vol_bytes = sizeof(float) * (tma ? tl.vol_elems() : b.plane() * (size_t)Dp);
     const size_t tab_bytes = sizeof(float) * b.plane() * (size_t)T;
@@ -256,7 +265,7 @@ int run_band(asw_ctx* ctx, const uint8_t* dl, const uint8_t* dr, int W, int H, i
             t.h_end(it);
         }
         t.e_agg = t.et.mark();
-        CUL(launch_wta_v2(s, tl, y0, y1, y0, va, d_rgba, d_d, d_conf));
+        CUL(launch_wta_v2(s, tl, y0, y1, y0, Dfull, va, d_rgba, d_d, d_conf, sh ? sh->min1 : nullptr, sh ? sh->min2 : nullptr, sh ? sh->arg : nullptr));
         t.e_wta = t.et.mark();
         if (ctx->keep_volume) {
             if ((st = ensure(ctx, ctx->vol_ref, sizeof(float) * (size_t)W * (y1 - y0) * D))) return st;
@@ -434,6 +443,37 @@ int asw_disparity_band_device(asw_ctx* ctx, const uint8_t* dl, const uint8_t* dr
     if (prm->ndisp > 256 && d_d) return fail(ctx, ASW_ERR_UNSUPPORTED, "disp_d is uint8: ndisp <= 256 required");
     CU(cudaSetDevice(ctx->device));
     return run_band(ctx, dl, dr, W, H, y0, y1, prm, d_rgba, d_d, d_conf, tm);
+}
+
+int asw_disparity_shard_device(asw_ctx* ctx, const uint8_t* dl, const uint8_t* dr, int W, int H, int y0, int y1, int d0, int d1,
+                               const asw_params* prm, float* d_min1, float* d_min2, int* d_arg, asw_timing* tm) {
+    int st = check_params(ctx, W, H, prm);
+    if (st) return st;
+    if (!dl || !dr || !d_min1 || !d_min2 || !d_arg) return fail(ctx, ASW_ERR_INVALID, "device pointer is NULL");
+    if (y0 < 0 || y1 > H || y0 >= y1) return fail(ctx, ASW_ERR_INVALID, "band must satisfy 0 <= y0 < y1 <= H");
+    if (d0 < 0 || d1 > prm->ndisp || d0 >= d1 || d0 % 64 != 0) return fail(ctx, ASW_ERR_INVALID, "shard must satisfy 0 <= d0 < d1 <= ndisp, d0 a multiple of 64");
+    CU(cudaSetDevice(ctx->device));
+    Shard sh;
+    sh.d0 = d0; sh.d1 = d1; sh.min1 = d_min1; sh.min2 = d_min2; sh.arg = d_arg;
+    const int keep = ctx->keep_volume;
+    ctx->keep_volume = 0;                                      // a shard's volume is partial: nothing to hand out
+    st = run_band(ctx, dl, dr, W, H, y0, y1, prm, nullptr, nullptr, nullptr, tm, &sh);
+    ctx->keep_volume = keep;
+    return st;
+}
+
+int asw_merge_shards(asw_ctx* ctx, int W, int rows, int ndisp, int nshards, const float* d_min1, const float* d_min2, const int* d_arg,
+                     uint8_t* d_rgba, uint8_t* d_d, float* d_conf) {
+    if (!ctx) return ASW_ERR_INVALID;
+    if (W <= 0 || rows <= 0 || ndisp <= 0 || nshards <= 0) return fail(ctx, ASW_ERR_INVALID, "W, rows, ndisp, nshards must be positive");
+    if (!d_min1 || !d_min2 || !d_arg) return fail(ctx, ASW_ERR_INVALID, "device pointer is NULL");
+    if (ndisp > 256 && d_d) return fail(ctx, ASW_ERR_UNSUPPORTED, "disp_d is uint8: ndisp <= 256 required");
+    CU(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)W * rows;
+    k_wta_merge<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_min1, d_min2, d_arg, nshards, n, ndisp, (uint32_t*)d_rgba, d_d, d_conf);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return ASW_OK;
 }
 
 int asw_disparity_device(asw_ctx* ctx, const uint8_t* dl, const uint8_t* dr, int W, int H, const asw_params* prm,

@@ -304,3 +304,48 @@ def test_full_size_cfg3_properties(ctx, oracle):
     b1 = run_fused(ctx, L, R, p, family=1, band=(1484, 1500))
     assert_bit_equal(b1["d"], full["d"][1484:1500], "cfg3 tiled vs basic kernels")
     assert_bit_equal(b1["conf"], full["conf"][1484:1500], "cfg3 tiled vs basic kernels (confidence)")
+
+
+# ---------------------------------------------------------------------------------------------
+# disparity shards (multi-GPU sharding without halo work): shard + merge == the unsharded call, bit for bit
+
+@pytest.mark.parametrize("W,H,D,it,shards,band", [
+    (200, 60, 130, 2, [(0, 64), (64, 128), (128, 130)], None),
+    (150, 50, 256, 1, [(0, 64), (64, 128), (128, 192), (192, 256)], None),
+    (150, 50, 256, 2, [(0, 128), (128, 256)], (10, 37)),
+    (97, 33, 61, 3, [(0, 61)], None),
+    (130, 40, 200, 1, [(0, 192), (192, 200)], (0, 40)),
+])
+def test_disparity_shards_equal_unsharded(ctx, W, H, D, it, shards, band):
+    from stereo_matchin_b200 import synth
+    L, R = synth.make_pair(W, H, D, seed=W + D)[:2]
+    p = P(ndisp=D, iterations=it)
+    full = run_fused(ctx, L, R, p, band=band)
+    y0, y1 = band if band else (0, H)
+    rows, n = y1 - y0, (y1 - y0) * W
+    dl, dr = ctx.to_device(L), ctx.to_device(R)
+    k = len(shards)
+    m1, m2, ar = ctx.alloc(4 * n * k), ctx.alloc(4 * n * k), ctx.alloc(4 * n * k)
+    for i, (d0, d1) in enumerate(shards):
+        ctx.disparity_shard_raw(dl.ptr, dr.ptr, W, H, p, (y0, y1), (d0, d1), m1.ptr + 4 * n * i, m2.ptr + 4 * n * i, ar.ptr + 4 * n * i)
+    o_rgba, o_d, o_conf = ctx.alloc(4 * n), ctx.alloc(n), ctx.alloc(4 * n)
+    ctx.merge_shards(W, rows, D, k, m1.ptr, m2.ptr, ar.ptr, o_rgba.ptr, o_d.ptr, o_conf.ptr)
+    ctx.sync()
+    assert_bit_equal(o_rgba.download((rows, W, 4), np.uint8), full["left"], "merged disparity image")
+    assert_bit_equal(o_d.download((rows, W), np.uint8), full["d"], "merged disparity index")
+    assert_bit_equal(o_conf.download((rows, W), np.float32), full["conf"], "merged confidence")
+    a = ar.download((k, rows, W), np.int32)
+    for i, (d0, d1) in enumerate(shards):
+        assert a[i].min() >= d0 and a[i].max() < d1, "a shard reports global disparity indices of its own range"
+
+
+def test_disparity_shard_errors(ctx):
+    from stereo_matchin_b200.api import AswError
+    L, R = crop_pair("teddy", 0, 0, 64, 32)
+    dl, dr = ctx.to_device(L), ctx.to_device(R)
+    b = ctx.alloc(4 * 64 * 32)
+    for shard in [(32, 61), (0, 62), (61, 61)]:          # d0 not a multiple of 64, d1 > ndisp, empty
+        with pytest.raises(AswError):
+            ctx.disparity_shard_raw(dl.ptr, dr.ptr, 64, 32, P(), (0, 32), shard, b.ptr, b.ptr, b.ptr)
+    with pytest.raises(AswError):                        # other radius -> not the TMA family
+        ctx.disparity_shard_raw(dl.ptr, dr.ptr, 64, 32, P(radius=4), (0, 32), (0, 61), b.ptr, b.ptr, b.ptr)
