@@ -6,8 +6,13 @@ The path shards without any mid-computation exchange:
     per iteration, so a band needs r*R real halo rows on each side (clipped at the frame border,
     where the reference's clamp-to-edge applies); the library shrinks the halo by R per iteration
     (asw_disparity_band_device), so the band is bit-identical to the same rows of a 1-GPU run.
-The only collective is one all-gather of the uint8 disparity bands / maps (NCCL on GPUs; the CPU
-tests run the same code over gloo).  The compute callback is injected so that the host logic can be
+  * disparity sharding -- planes of the cost volume never interact during aggregation, so a rank can own
+    the disparities [d0, d1) of (a band of) a frame with NO halo work; it returns per pixel the partial
+    winner-take-all triple (min1, min2, argmin) and the triples are merged after one all-gather
+    (asw_disparity_shard_device / asw_merge_shards).  A 2-D grid (row bands x disparity shards) keeps the
+    halo overhead of an 8-GPU run of a 4K frame at +4 % instead of +31 %.
+The only collectives are all-gathers of results: uint8 disparity bands / maps, or the 12-byte partial
+triples of disparity shards (NCCL on GPUs; the CPU tests run the same code over gloo).  The compute callback is injected so that the host logic can be
 tested without a GPU; the product passes the CUDA library's band entry point.
 """
 from __future__ import annotations
@@ -131,5 +136,106 @@ def cuda_band_fn(ctx, params) -> BandFn:
         ctx.disparity_raw(dl.data_ptr(), dr.data_ptr(), W, H, params, None, out.data_ptr(), None, band=(y0, y1))
         ctx.sync()
         return out.cpu().numpy()
+
+    return fn
+
+
+# ---- 2-D sharding of one frame: row bands x disparity shards -------------------------------------------
+
+def shard_grid(world: int, ndisp: int, window: int = 64) -> Tuple[int, int]:
+    """(row bands, disparity shards) for `world` ranks: as many disparity shards as there are 64-disparity
+    windows (no halo work), the rest of the ranks as row bands.  world must factor accordingly."""
+    nwin = max(1, (ndisp + window - 1) // window)
+    nd = 1
+    for cand in range(min(world, nwin), 0, -1):
+        if world % cand == 0 and nwin % cand == 0:
+            nd = cand
+            break
+    return world // nd, nd
+
+
+def disparity_shards(ndisp: int, nd: int, window: int = 64) -> List[Tuple[int, int]]:
+    """nd contiguous disparity ranges whose starts are multiples of `window` (the library's requirement)."""
+    nwin = (ndisp + window - 1) // window
+    if nd < 1 or nd > nwin:
+        raise ValueError("between 1 and ceil(ndisp / window) disparity shards")
+    out = []
+    for i in range(nd):
+        w0, w1 = (nwin * i) // nd, (nwin * (i + 1)) // nd
+        out.append((w0 * window, min(w1 * window, ndisp)))
+    return out
+
+
+def rank_shard(rank: int, world: int, H: int, ndisp: int) -> Tuple[Tuple[int, int], Tuple[int, int], int, int]:
+    """((y0, y1), (d0, d1), band index, shard index) of `rank`; ranks of one band are consecutive."""
+    nb, nd = shard_grid(world, ndisp)
+    bi, di = rank // nd, rank % nd
+    return row_bands(H, nb)[bi], disparity_shards(ndisp, nd)[di], bi, di
+
+
+def merge_triples(min1: np.ndarray, min2: np.ndarray, arg: np.ndarray):
+    """Numpy statement of Min2::merge over the leading (shard) axis, shards in ascending disparity order:
+    the result equals one sequential two-minimum scan over all disparities (lowest index wins ties)."""
+    cur, last, a = min1[0].copy(), min2[0].copy(), arg[0].copy()
+    for s in range(1, min1.shape[0]):
+        oc, ol, oa = min1[s], min2[s], arg[s]
+        take = (oc < cur) | ((oc == cur) & (oa < a))
+        lo = np.where(take, oc, cur)
+        other = np.where(take, cur, oc)
+        last = np.minimum(other, np.minimum(last, ol))
+        a = np.where(take, oa, a)
+        cur = lo
+    return cur, last, a
+
+
+ShardFn = Callable[[np.ndarray, np.ndarray, Tuple[int, int], Tuple[int, int]], Tuple[np.ndarray, np.ndarray, np.ndarray]]
+
+
+def disparity_2d_sharded(left: np.ndarray, right: np.ndarray, ndisp: int, rank: int, world: int, compute_shard: ShardFn,
+                         device="cpu", group=None):
+    """One frame on a (row bands x disparity shards) grid of ranks.  `compute_shard(left, right, (y0, y1), (d0, d1))`
+    returns the partial (min1, min2, argmin) float32 / float32 / int32 arrays of shape (y1-y0, W).  One all-gather of
+    the triples, then every rank merges each band's shards.  Returns (argmin map uint8/int32 (H, W), confidence (H, W)).
+    H must be divisible by the number of bands."""
+    import torch
+    import torch.distributed as dist
+
+    H, W, _ = left.shape
+    nb, nd = shard_grid(world, ndisp)
+    if H % nb:
+        raise ValueError("H must be divisible by the number of row bands")
+    (y0, y1), (d0, d1), _, _ = rank_shard(rank, world, H, ndisp)
+    m1, m2, a = compute_shard(left, right, (y0, y1), (d0, d1))
+    rows = y1 - y0
+    mine = torch.from_numpy(np.stack([m1.astype(np.float32).view(np.int32), m2.astype(np.float32).view(np.int32), a.astype(np.int32)])).to(device)
+    if world > 1:
+        allp = torch.empty((world,) + tuple(mine.shape), dtype=torch.int32, device=mine.device)
+        dist.all_gather_into_tensor(allp.view(-1), mine.contiguous().view(-1), group=group)
+    else:
+        allp = mine.unsqueeze(0)
+    allp = allp.cpu().numpy().reshape(nb, nd, 3, rows, W)
+    cur, last, arg = merge_triples(allp[:, :, 0].view(np.float32).transpose(1, 0, 2, 3).reshape(nd, H, W),
+                                   allp[:, :, 1].view(np.float32).transpose(1, 0, 2, 3).reshape(nd, H, W),
+                                   allp[:, :, 2].transpose(1, 0, 2, 3).reshape(nd, H, W))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        conf = ((last - cur) / last).astype(np.float32)
+    return arg, conf
+
+
+def cuda_shard_fn(ctx, params) -> ShardFn:
+    """The product's compute callback: asw_disparity_shard_device on this rank's GPU."""
+    import torch
+
+    def fn(left, right, band, dshard):
+        H, W, _ = left.shape
+        rows = band[1] - band[0]
+        dl = torch.from_numpy(np.ascontiguousarray(left)).cuda()
+        dr = torch.from_numpy(np.ascontiguousarray(right)).cuda()
+        m1 = torch.empty((rows, W), dtype=torch.float32, device="cuda")
+        m2 = torch.empty_like(m1)
+        a = torch.empty((rows, W), dtype=torch.int32, device="cuda")
+        ctx.disparity_shard_raw(dl.data_ptr(), dr.data_ptr(), W, H, params, band, dshard, m1.data_ptr(), m2.data_ptr(), a.data_ptr())
+        ctx.sync()
+        return m1.cpu().numpy(), m2.cpu().numpy(), a.cpu().numpy()
 
     return fn
