@@ -142,6 +142,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--iterations", type=int, default=7)
+    ap.add_argument("--grid", default="", help="cfg4: force the (row bands)x(disparity shards) grid, e.g. 4x2")
+    ap.add_argument("--bands-only", action="store_true", help="cfg4: shard by row bands only (default: row bands x disparity shards)")
     ap.add_argument("--family", type=int, default=0, help="0 = TMA-fed kernels (default), 1 = basic kernels, 2 = tiled kernels without TMA")
     ap.add_argument("--cpu-rows", type=int, default=400, help="rows of the pair the CPU baseline sample covers")
     ap.add_argument("--ref-rows", type=int, default=400)
@@ -177,10 +179,21 @@ def main():
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
 
     # ---- inputs: pinned host copies and device-resident copies --------------------------------
+    dshard, grid = None, (world, 1)
     if band_mode:
+        from stereo_matchin_b200 import sharding
         pairs = [synth.make_config(cfg, 0)[:2]]                      # every rank holds the full frame
-        y0, y1 = (H * rank) // world, (H * (rank + 1)) // world
-        band, out_rows = (y0, y1), y1 - y0
+        grid = sharding.shard_grid(world, D) if args.family == 0 and not args.bands_only else (world, 1)
+        if args.grid:
+            grid = tuple(int(v) for v in args.grid.lower().split("x"))
+            assert grid[0] * grid[1] == world, "--grid must multiply to the number of ranks"
+        if H % grid[0]:
+            grid = (world, 1)
+        if grid[1] > 1:     # 2-D grid: row bands x disparity shards (no halo work along d), ranks of a band are consecutive
+            band, dshard, _, _ = sharding.rank_shard(rank, world, H, D, grid)
+        else:
+            band = ((H * rank) // world, (H * (rank + 1)) // world)
+        out_rows = band[1] - band[0]
     else:
         pairs = [synth.make_config(cfg, rank * pairs_per_rank + i)[:2] for i in range(pairs_per_rank)]
         band, out_rows = None, H
@@ -191,12 +204,34 @@ def main():
     dev_d = [torch.empty((out_rows, W), dtype=torch.uint8, device="cuda") for _ in pairs]
     gather = torch.empty((world, len(pairs), out_rows, W), dtype=torch.uint8, device="cuda") if world > 1 and not band_mode else None
     gather_band = torch.empty((H, W), dtype=torch.uint8, device="cuda") if world > 1 and band_mode else None
-    units_per_step_rank = W * out_rows * D * len(pairs)              # pix*disp this rank produces per step
+    nd = grid[1]
+    if dshard is not None:  # partial WTA triples of this rank, the gathered triples of all ranks, this band's shards re-laid out
+        parts = torch.empty((3, out_rows, W), dtype=torch.float32, device="cuda")
+        allparts = torch.empty((world, 3, out_rows, W), dtype=torch.float32, device="cuda")
+        gather_band = torch.empty((world, out_rows, W), dtype=torch.uint8, device="cuda")
+    units_per_step_rank = W * out_rows * ((dshard[1] - dshard[0]) if dshard else D) * len(pairs)   # pix*disp this rank produces per step
     torch.cuda.synchronize()
 
     stage_log = []   # per-stage CUDA-event times of every hot-path call made inside the timed region
 
+    def shard_step(timing):
+        """cfg4 on a 2-D grid: aggregate this rank's (band, disparity shard), all-gather the partial WTA triples (the one
+        real exchange step of this sharding: 12 B per pixel and rank), merge this band's shards, all-gather the bands."""
+        l, rr = dev_in[0]
+        tmr = ctx.disparity_shard_raw(l.data_ptr(), rr.data_ptr(), W, H, params, band, dshard, parts[0].data_ptr(), parts[1].data_ptr(),
+                                      parts[2].data_ptr(), timing=timing)
+        with torch.cuda.stream(stream):
+            dist.all_gather_into_tensor(allparts, parts)
+            b0 = (rank // nd) * nd
+            mine = allparts[b0:b0 + nd].permute(1, 0, 2, 3).contiguous()           # [3][shard][rows][W]
+            ctx.merge_shards(W, out_rows, D, nd, mine[0].data_ptr(), mine[1].data_ptr(), mine[2].data_ptr(), None, dev_d[0].data_ptr(), None)
+            dist.all_gather_into_tensor(gather_band, dev_d[0])                      # rank b*nd holds band b
+        return tmr
+
     def step_device():
+        if dshard is not None:
+            stage_log.append(shard_step(True))
+            return
         for (l, rr), o in zip(dev_in, dev_d):
             # timing=True: the library brackets every kernel group with events on its own stream (and waits for
             # them at the end of the call, a ~20 us host gap per call that stays inside the timed region)
@@ -209,6 +244,15 @@ def main():
                     dist.all_gather_into_tensor(gather, torch.stack(dev_d) if len(dev_d) > 1 else dev_d[0].unsqueeze(0))
 
     def step_host():
+        if dshard is not None:
+            with torch.cuda.stream(stream):
+                dev_in[0][0].copy_(host_in[0][0], non_blocking=True)
+                dev_in[0][1].copy_(host_in[0][1], non_blocking=True)
+            shard_step(False)
+            with torch.cuda.stream(stream):
+                host_d[0].copy_(dev_d[0], non_blocking=True)
+            stream.synchronize()
+            return
         for (l, rr), o, of in zip(host_in, host_d, host_full_d):
             if band_mode:   # upload, run the band on device pointers, download the band
                 with torch.cuda.stream(stream):
@@ -271,7 +315,8 @@ def main():
         rows_mean = out_rows
         if band_mode:   # halo rows computed per pass, averaged over the r iterations
             rows_mean = float(np.mean([min(H, band[1] + (r - 1 - it) * 16) - max(0, band[0] - (r - 1 - it) * 16) for it in range(r)]))
-        pass_flops = 4.0 * T_TAPS * W * rows_mean * D
+        D_rank = (dshard[1] - dshard[0]) if dshard else D             # disparities this rank aggregates
+        pass_flops = 4.0 * T_TAPS * W * rows_mean * D_rank
         # V pass = main kernel + two small launches (diagonal fix-up, edge padding): the dominant KERNEL is the main one
         v_ms, h_ms = tm["vagg_mean_ms"] - tm["vfix_mean_ms"], tm["hagg_mean_ms"]
         tma = args.family == 0                                   # radius 16: the TMA-fed kernels (D padded to 128 internally)
@@ -291,7 +336,7 @@ def main():
         achieved = pass_flops / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
         peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
         hbm_peak = json.load(open(peaks_file)).get("hbm_gbs") if os.path.exists(peaks_file) else 6650.0
-        Dp = (D + 63) // 64 * 64 if args.family == 0 else (D + 31) // 32 * 32
+        Dp = (D_rank + 63) // 64 * 64 if args.family == 0 else (D + 31) // 32 * 32
         pass_bytes = 3.0 * 4 * W * rows_mean * Dp      # tiled kernels: read cost + read denominator + write cost
         traffic, traffic_src = None, None                       # DRAM bytes per launch of that kernel, from the committed ncu --set full capture
         tfiles = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_traffic.json")) if os.path.isdir(os.path.join(ROOT, "profiles")) else []
@@ -304,7 +349,7 @@ def main():
                     "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": pass_bytes,
                     "timing": "CUDA events on the library's stream around every launch group, mean over the timed region",
                     "peak_source": peak_src, "measured_ffma_microbench": ffma,
-                    "whole_path_frac": alg_flops(W, rows_mean, D, r) / (tm["total_ms"] * 1e-3) / 1e12 / peak,
+                    "whole_path_frac": alg_flops(W, rows_mean, D_rank, r) / (tm["total_ms"] * 1e-3) / 1e12 / peak,
                     "v_pass_ms": v_ms, "h_pass_ms": h_ms,
                     "hbm": {"algorithmic_gbs": pass_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0, "peak_gbs": hbm_peak,
                             "bytes_per_pass": pass_bytes}}
@@ -345,7 +390,8 @@ def main():
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
             "scaling": "strong" if band_mode else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {desc}", "W": W, "H": H, "ndisp": D, "radius": 16, "iterations": r,
-                       "pairs_per_rank": len(pairs), "sharding": ("row bands + shrinking halo, all-gather of bands" if band_mode
+                       "pairs_per_rank": len(pairs), "sharding": (("%d row bands x %d disparity shards, all-gather of partial WTA triples + bands" % grid) if dshard is not None
+                                                                  else "row bands + shrinking halo, all-gather of bands" if band_mode
                                                                   else "pairs (independent), all-gather of disparity maps"),
                        "l2": "inputs larger than L2: every pass streams a %.2f GB cost volume" % (4.0 * W * H * Dp / 1e9),
                        "kernel_family": {0: "tma", 1: "basic", 2: "tiled"}[args.family]},

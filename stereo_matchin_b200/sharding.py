@@ -166,9 +166,9 @@ def disparity_shards(ndisp: int, nd: int, window: int = 64) -> List[Tuple[int, i
     return out
 
 
-def rank_shard(rank: int, world: int, H: int, ndisp: int) -> Tuple[Tuple[int, int], Tuple[int, int], int, int]:
+def rank_shard(rank: int, world: int, H: int, ndisp: int, grid: Tuple[int, int] | None = None) -> Tuple[Tuple[int, int], Tuple[int, int], int, int]:
     """((y0, y1), (d0, d1), band index, shard index) of `rank`; ranks of one band are consecutive."""
-    nb, nd = shard_grid(world, ndisp)
+    nb, nd = grid if grid else shard_grid(world, ndisp)
     bi, di = rank // nd, rank % nd
     return row_bands(H, nb)[bi], disparity_shards(ndisp, nd)[di], bi, di
 
