@@ -142,9 +142,11 @@ def cuda_band_fn(ctx, params) -> BandFn:
 
 # ---- 2-D sharding of one frame: row bands x disparity shards -------------------------------------------
 
-def shard_grid(world: int, ndisp: int, window: int = 64) -> Tuple[int, int]:
-    """(row bands, disparity shards) for `world` ranks: as many disparity shards as there are 64-disparity
-    windows (no halo work), the rest of the ranks as row bands.  world must factor accordingly."""
+def shard_grid(world: int, ndisp: int, window: int = 128) -> Tuple[int, int]:
+    """(row bands, disparity shards) for `world` ranks: as many disparity shards as there are 128-disparity
+    windows (no halo work), the rest of the ranks as row bands.  (Measured on the 4K x 256 frame: shards of 64
+    disparities lose to 128 because the per-tile fixed costs of the vertical pass and the replicated weight
+    tables weigh more: 4 ranks 2x2 39.1 ms vs 1x4 43.7 ms; 8 ranks 4x2 23.0, 2x4 23.2, 8x1 24.9 ms.)"""
     nwin = max(1, (ndisp + window - 1) // window)
     nd = 1
     for cand in range(min(world, nwin), 0, -1):
@@ -192,7 +194,7 @@ ShardFn = Callable[[np.ndarray, np.ndarray, Tuple[int, int], Tuple[int, int]], T
 
 
 def disparity_2d_sharded(left: np.ndarray, right: np.ndarray, ndisp: int, rank: int, world: int, compute_shard: ShardFn,
-                         device="cpu", group=None):
+                         device="cpu", group=None, grid: Tuple[int, int] | None = None):
     """One frame on a (row bands x disparity shards) grid of ranks.  `compute_shard(left, right, (y0, y1), (d0, d1))`
     returns the partial (min1, min2, argmin) float32 / float32 / int32 arrays of shape (y1-y0, W).  One all-gather of
     the triples, then every rank merges each band's shards.  Returns (argmin map uint8/int32 (H, W), confidence (H, W)).
@@ -201,10 +203,10 @@ def disparity_2d_sharded(left: np.ndarray, right: np.ndarray, ndisp: int, rank: 
     import torch.distributed as dist
 
     H, W, _ = left.shape
-    nb, nd = shard_grid(world, ndisp)
+    nb, nd = grid if grid else shard_grid(world, ndisp)
     if H % nb:
         raise ValueError("H must be divisible by the number of row bands")
-    (y0, y1), (d0, d1), _, _ = rank_shard(rank, world, H, ndisp)
+    (y0, y1), (d0, d1), _, _ = rank_shard(rank, world, H, ndisp, (nb, nd))
     m1, m2, a = compute_shard(left, right, (y0, y1), (d0, d1))
     rows = y1 - y0
     mine = torch.from_numpy(np.stack([m1.astype(np.float32).view(np.int32), m2.astype(np.float32).view(np.int32), a.astype(np.int32)])).to(device)

@@ -65,7 +65,7 @@ def _worker(rank, world, port, mode, q):
     try:
         if mode == "grid":
             L, R = crop_pair("teddy", 150, 100, 150, 64)
-            arg, conf = sharding.disparity_2d_sharded(L, R, 128, rank, world, _oracle_shard)
+            arg, conf = sharding.disparity_2d_sharded(L, R, 128, rank, world, _oracle_shard, grid=(2, 2))
             q.put((rank, np.stack([arg.astype(np.float32), conf])))
         elif mode == "bands":
             L, R = crop_pair("teddy", 40, 0, 120, 151)      # 151 rows: uneven bands
@@ -138,7 +138,8 @@ def test_2d_sharding_matches_single_process():
     """4 ranks = 2 row bands x 2 disparity shards: merged result == unsharded oracle (indices and confidence)."""
     from oracle import asw_oracle as O
     from stereo_matchin_b200 import sharding
-    assert sharding.shard_grid(4, 128) == (2, 2) and sharding.shard_grid(8, 256) == (2, 4) and sharding.shard_grid(4, 130) == (4, 1)
+    assert sharding.shard_grid(4, 256) == (2, 2) and sharding.shard_grid(8, 256) == (4, 2) and sharding.shard_grid(4, 130) == (2, 2)
+    assert sharding.shard_grid(4, 128, window=64) == (2, 2) and sharding.shard_grid(3, 256) == (3, 1)
     assert sharding.disparity_shards(256, 4) == [(0, 64), (64, 128), (128, 192), (192, 256)]
     assert sharding.disparity_shards(130, 3) == [(0, 64), (64, 128), (128, 130)]
     L, R = crop_pair("teddy", 150, 100, 150, 64)
