@@ -39,7 +39,7 @@ if os.path.exists(rep):
     for r in rows[2:]:
         name = r[hd["Kernel Name"]]
         key = "k_vagg_v2" if "k_vagg_v2<8, 0>" in name or "k_vagg_v2<(int)8, (bool)0>" in name else \
-              "k_hagg_split" if "k_hagg_split<0>" in name or "k_hagg_split<(bool)0>" in name else None
+              "k_hagg_split" if "k_hagg_split<0" in name or "k_hagg_split<(bool)0" in name else None
         if key:
             def gb(col):
                 v, u = float(r[hd[col]].replace(",", "")), rows[1][hd[col]]
