@@ -349,3 +349,21 @@ def test_disparity_shard_errors(ctx):
             ctx.disparity_shard_raw(dl.ptr, dr.ptr, 64, 32, P(), (0, 32), shard, b.ptr, b.ptr, b.ptr)
     with pytest.raises(AswError):                        # other radius -> not the TMA family
         ctx.disparity_shard_raw(dl.ptr, dr.ptr, 64, 32, P(radius=4), (0, 32), (0, 61), b.ptr, b.ptr, b.ptr)
+
+
+def test_sharding_callbacks_single_process(ctx):
+    """The product's sharding callbacks (stereo_matchin_b200.sharding.cuda_band_fn / cuda_shard_fn) on one rank."""
+    from stereo_matchin_b200 import sharding, synth
+    L, R = synth.make_pair(160, 48, 128, seed=21)[:2]
+    p = P(ndisp=128, iterations=2)
+    full = run_fused(ctx, L, R, p)
+    band = sharding.cuda_band_fn(ctx, p)(L, R, 8, 40)
+    assert_bit_equal(band, full["d"][8:40], "cuda_band_fn")
+    arg, conf = sharding.disparity_2d_sharded(L, R, 128, 0, 1, sharding.cuda_shard_fn(ctx, p))
+    assert_bit_equal(arg.astype(np.uint8), full["d"], "cuda_shard_fn + merge_triples: disparity")
+    assert_bit_equal(conf, full["conf"], "cuda_shard_fn + merge_triples: confidence")
+    # two shards merged on the host equal the unsharded result as well
+    fn = sharding.cuda_shard_fn(ctx, p)
+    parts = [fn(L, R, (0, 48), ds) for ds in sharding.disparity_shards(128, 2)]
+    cur, last, a = sharding.merge_triples(np.stack([q[0] for q in parts]), np.stack([q[1] for q in parts]), np.stack([q[2] for q in parts]))
+    assert_bit_equal(a.astype(np.uint8), full["d"], "host merge of two shards")
