@@ -1,0 +1,326 @@
+// taploop.cu -- stand-alone probe of the tap loops of the aggregation kernels (no global traffic, no TMA):
+// the inner loops of k_hagg_split / k_vagg_v2 run on shared memory filled once, with pieces switched off
+// by template flags, at 2-4 warps per scheduler.  Reports SM cycles (clock64 on the SM) per warp and tap and
+// the implied FMA-pipe utilisation, so that the limiter of the loop (FMA pipe, LSU, issue, latency) can be
+// told apart from the memory system.  Built by scripts/build_taploop.sh; measurement helper, not product.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdint.h>
+
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float4 lds128(const void* p) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+    return v;
+}
+__device__ __forceinline__ float lds32(const void* p) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(smem_u32(p)));
+    return v;
+}
+
+constexpr int kT = 33;
+
+// ---------------------------------------------------------------------------------------------------
+// H loop: thread = 8 x  x 4 d, taps unrolled, window slides in registers (k_hagg_split).
+//   FLAGS bit 0: left-weight loads per tap   bit 1: right-weight loads per tap   bit 2: cost loads per tap
+//         bit 3: math   bit 4: remapped lanes (4 x-runs x 8 quads per warp)
+template <int FLAGS, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_h(float* out, long long* cyc, int nsteps, int smem_floats) {
+    extern __shared__ __align__(128) float sm[];
+    for (int i = threadIdx.x; i < smem_floats; i += blockDim.x) sm[i] = 1.0f + (float)(i & 1023) * 1e-4f;
+    __syncthreads();
+    constexpr int DPC = 128, W_BLK = kT * 32, C_SLOT = 32 * DPC;
+    float* sC = sm;
+    const int tid = threadIdx.x;
+    int xr, dq;
+    if (FLAGS & 16) { const int hw = tid >> 5, hl = tid & 31, Q = hl >> 2; xr = 2 * (hw >> 1) + ((hl >> 1) & 1); dq = (4 * (Q & 1) + 2 * ((Q >> 1) & 1) + 8 * (Q >> 2) + 16 * (hw & 1) + (hl & 3)) & 31; }
+    else { xr = tid / 32; dq = tid % 32; }
+    f32x2 acc[8][2];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { acc[j][0] = pack2(1e-5f, 1e-5f); acc[j][1] = pack2(1e-5f, 1e-5f); }
+    const long long t0 = clock64();
+    for (int m = 0; m < nsteps; m++) {
+        auto c_ptr = [&](int cidx) -> const float4* {
+            const int slot = (m + (cidx >> 5)) % 3;
+            return reinterpret_cast<const float4*>(sC + (slot * C_SLOT + (cidx & 31) * DPC + 4 * dq) % smem_floats);
+        };
+        const int colp = 32 * m + 8 * xr - 4 * dq - 4 + 160;
+        const float* wr_ptr[3];
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            const int cq = colp + 4 * q;
+            wr_ptr[q] = sm + ((((cq >> 5) % 6) * W_BLK + (cq & 31) + 12288) % (smem_floats - 1152) & ~3);
+        }
+        const float* wl_ptr = sm + (((m & 1) * W_BLK + 8 * xr + 8192) % (smem_floats - 1152) & ~3);
+        float4 win[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) win[j] = lds128(c_ptr(8 * xr + j));
+        float4 la, lb, r0, r1, r2;
+        if (!(FLAGS & 1)) { la = lds128(wl_ptr); lb = lds128(wl_ptr + 4); }
+        if (!(FLAGS & 2)) { r0 = lds128(wr_ptr[0]); r1 = lds128(wr_ptr[1]); r2 = lds128(wr_ptr[2]); }
+#pragma unroll
+        for (int i = 0; i < kT; i++) {
+            if (FLAGS & 1) { la = lds128(wl_ptr + i * 32); lb = lds128(wl_ptr + i * 32 + 4); }
+            if (FLAGS & 2) { r0 = lds128(wr_ptr[0] + i * 32); r1 = lds128(wr_ptr[1] + i * 32); r2 = lds128(wr_ptr[2] + i * 32); }
+            const float wl[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};
+            const float wr[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
+            if (FLAGS & 8) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const float4 c4 = win[(j + i) & 7];
+                    const f32x2 c2[2] = {pack2(c4.x, c4.y), pack2(c4.z, c4.w)};
+                    const f32x2 wlj = pack2(wl[j], wl[j]);
+#pragma unroll
+                    for (int mp = 0; mp < 2; mp++) {
+                        const f32x2 ww = (j & 1) ? mul2(wlj, pack2(wr[j - 2 * mp + 4], wr[j - 2 * mp + 3]))
+                                                 : pack2(__fmul_rn(wl[j], wr[j - 2 * mp + 4]), __fmul_rn(wl[j], wr[j - 2 * mp + 3]));
+                        acc[j][mp] = fma2(ww, c2[mp], acc[j][mp]);
+                    }
+                }
+            } else {
+                // keep the loads alive
+#pragma unroll
+                for (int j = 0; j < 8; j++) if (wl[j] == 123.f || wr[j] == 77.f) acc[j][0] ^= 1ull;
+                if (win[i & 7].x == 55.f) acc[0][1] ^= 1ull;
+            }
+            if ((FLAGS & 4) && i + 1 < kT) win[i & 7] = lds128(c_ptr(8 * xr + 8 + i));
+        }
+    }
+    const long long t1 = clock64();
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { float a, b; unpack2(acc[j][0], a, b); s += a + b; unpack2(acc[j][1], a, b); s += a + b; }
+    if (s == 123.456f) out[0] = s;
+    __shared__ unsigned long long tmin, tmax;
+    if (threadIdx.x == 0) { tmin = ~0ull; tmax = 0ull; }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { atomicMin(&tmin, (unsigned long long)t0); atomicMax(&tmax, (unsigned long long)t1); }
+    __syncthreads();
+    if (threadIdx.x == 0) cyc[blockIdx.x] = (long long)(tmax - tmin);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// V loop: thread = 4-long diagonal x 2 diagonals x 8 rows; a step = 4 input rows (k_vagg_v2 math warps).
+//   FLAGS bit 0: left-weight loads   bit 1: right-weight loads   bit 2: cost loads   bit 3: math
+//         bit 4: remapped lanes
+template <int FLAGS, int NWARP, int MINB>
+__global__ void __launch_bounds__(NWARP * 32, MINB) k_v(float* out, long long* cyc, int nsteps, int smem_floats) {
+    extern __shared__ __align__(128) float sm[];
+    for (int i = threadIdx.x; i < smem_floats; i += blockDim.x) sm[i] = 1.0f + (float)(i & 1023) * 1e-4f;
+    __syncthreads();
+    constexpr int XW = 32, WRC = 96, kVCols = 68, kVWL = 8 * 4 * XW, kVWR = 8 * WRC * 4, STAGE = kVWL + kVWR + 4 * XW * kVCols;
+    const int tid = threadIdx.x, w = (tid >> 5) & 7, lane = tid & 31;
+    int tw, el[2];
+    if (FLAGS & 16) { tw = (w & 3) + 4 * ((lane >> 1) & 1); el[0] = 2 * (lane >> 2) + (lane & 1) + 16 * ((lane >> 1) & 1) + 16 * (w >> 2); el[1] = (el[0] + 32) & 63; }
+    else { tw = w; el[0] = lane; el[1] = lane + 32; }
+    f32x2 acc[8][2][2];
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+#pragma unroll
+        for (int jp = 0; jp < 2; jp++)
+#pragma unroll
+            for (int ee = 0; ee < 2; ee++) acc[k][jp][ee] = pack2(1e-5f, 1e-5f);
+    const int nstage = smem_floats / STAGE;
+    if ((FLAGS & 64) && (tid >> 5) >= 4) __nanosleep(400);
+    f32x2 c2[2][4][2][2];
+    auto load_costs = [&](int set, int g) {
+        const float* sC = sm + (g % nstage) * STAGE + kVWL + kVWR + (4 * tw) * kVCols;
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int jp = 0; jp < 2; jp++)
+#pragma unroll
+                for (int ee = 0; ee < 2; ee++) {
+                    const float* p = sC + (r * XW + 2 * jp) * kVCols + el[ee] + 2 * jp;
+                    c2[set][r][jp][ee] = (FLAGS & 4) ? pack2(lds32(p), lds32(p + kVCols + 1)) : pack2(1.0f + r, 2.0f + jp);
+                }
+    };
+    const long long t0 = clock64();
+    if (FLAGS & 32) load_costs(0, 0);
+    for (int g2 = 0; g2 < nsteps; g2 += 2) {
+#pragma unroll
+      for (int par = 0; par < 2; par++) {
+        const int g = g2 + par;
+        const float* sWL = sm + (g % nstage) * STAGE;
+        const float* sWR = sWL + kVWL;
+        if (!(FLAGS & 32)) load_costs(par, g);
+        float4 r0 = make_float4(1.f, 1.01f, 1.02f, 1.03f), r1 = make_float4(1.1f, 1.11f, 1.12f, 1.13f), l4 = make_float4(.9f, .91f, .92f, .93f);
+        if (!(FLAGS & 2)) { r0 = lds128(sWR + (4 * tw + 63 - el[0]) * 4); r1 = lds128(sWR + (4 * tw + 63 - el[1]) * 4); }
+        if (!(FLAGS & 1)) l4 = lds128(sWL + 4 * tw);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if ((FLAGS & 32) && k == 4) load_costs(par ^ 1, g + 1);
+            if (FLAGS & 2) { r0 = lds128(sWR + (k * WRC + 4 * tw + 63 - el[0]) * 4); r1 = lds128(sWR + (k * WRC + 4 * tw + 63 - el[1]) * 4); }
+            const float wr[2][4] = {{r0.x, r0.y, r0.z, r0.w}, {r1.x, r1.y, r1.z, r1.w}};
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                if (FLAGS & 1) l4 = lds128(sWL + (k * 4 + r) * XW + 4 * tw);
+                const f32x2 wl2[2] = {pack2(l4.x, l4.y), pack2(l4.z, l4.w)};
+#pragma unroll
+                for (int ee = 0; ee < 2; ee++) {
+                    const f32x2 wrr = pack2(wr[ee][r], wr[ee][r]);
+#pragma unroll
+                    for (int jp = 0; jp < 2; jp++) {
+                        if (FLAGS & 8) {
+                            const f32x2 ww = mul2(wl2[jp], wrr);
+                            acc[k][jp][ee] = fma2(ww, c2[par][r][jp][ee], acc[k][jp][ee]);
+                        } else {
+                            if (wr[ee][r] == 77.f || l4.x == 55.f) acc[k][jp][ee] ^= c2[par][r][jp][ee];
+                        }
+                    }
+                }
+            }
+        }
+      }
+    }
+    const long long t1 = clock64();
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+#pragma unroll
+        for (int jp = 0; jp < 2; jp++)
+#pragma unroll
+            for (int ee = 0; ee < 2; ee++) { float a, b; unpack2(acc[k][jp][ee], a, b); s += a + b; }
+    if (s == 123.456f) out[0] = s;
+    __shared__ unsigned long long tmin, tmax;
+    if (threadIdx.x == 0) { tmin = ~0ull; tmax = 0ull; }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { atomicMin(&tmin, (unsigned long long)t0); atomicMax(&tmax, (unsigned long long)t1); }
+    __syncthreads();
+    if (threadIdx.x == 0) cyc[blockIdx.x] = (long long)(tmax - tmin);
+}
+
+static int g_sms = 0;
+static float* g_out;
+static long long* g_cyc;
+
+// ---------------------------------------------------------------------------------------------------
+// LDS cost: 16 unrolled loads per iteration, every loaded register consumed by FFMAs (2 per LDS.128, FMA pipe),
+// pattern of lane addresses (index of the WIDTH-byte chunk a lane reads):
+//   0 distinct contiguous   1 full broadcast   2 groups of 4 adjacent lanes share (8 distinct)   3 groups of 8 adjacent (4 distinct)
+//   4 lanes l, l+16 share (16 distinct)   5 lanes l, l+8, l+16, l+24 share (8 distinct)   6 pairs of adjacent lanes (16 distinct)
+//   7 lanes l, l+8 share inside each half warp, halves distinct (16 distinct)   8 groups of 2 adjacent... of 16 (2 distinct)
+template <int WIDTH, int PAT>
+__global__ void __launch_bounds__(256) k_lds(float* out, long long* cyc, int iters, int smem_floats) {
+    extern __shared__ __align__(128) float sm[];
+    for (int i = threadIdx.x; i < smem_floats; i += blockDim.x) sm[i] = (float)(i & 255) * 1e-3f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int idx = PAT == 0 ? lane : PAT == 1 ? 0 : PAT == 2 ? lane >> 2 : PAT == 3 ? lane >> 3 : PAT == 4 ? (lane & 15) : PAT == 5 ? (lane & 7)
+                    : PAT == 6 ? (lane >> 1) : PAT == 7 ? (lane & 7) + 8 * (lane >> 4) : PAT == 8 ? (lane >> 4)
+                    : PAT == 9 ? (lane & 3) : PAT == 10 ? (lane & 1) : PAT == 11 ? ((lane >> 1) & 1) : PAT == 12 ? ((lane >> 2) & 1)
+                    : PAT == 13 ? ((lane >> 3) & 1) : PAT == 14 ? ((lane >> 1) & 3) : PAT == 15 ? ((lane >> 2) & 3) : PAT == 16 ? (lane >> 1) ^ 1
+                    : PAT == 17 ? 15 - (lane >> 1) : (lane & 1) + 2 * (lane >> 2);
+    const unsigned base0 = smem_u32(sm) + (unsigned)(idx * WIDTH) + (unsigned)(warp & 7) * 1024u;
+    float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) {
+        const unsigned base = base0 + ((unsigned)(it & 1) << 13);
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            const unsigned a = base + (u & 7) * 512u + ((u & 8) ? 16384u : 0u);
+            if (WIDTH == 16) {
+                float x, y, z, w;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x), "=f"(y), "=f"(z), "=f"(w) : "r"(a));
+                if (u & 1) { f0 = __fmaf_rn(x, y, f0); f1 = __fmaf_rn(z, w, f1); } else { f2 = __fmaf_rn(x, y, f2); f3 = __fmaf_rn(z, w, f3); }
+            } else if (WIDTH == 8) {
+                float x, y;
+                asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(x), "=f"(y) : "r"(a));
+                if (u & 1) f0 = __fmaf_rn(x, y, f0); else f2 = __fmaf_rn(x, y, f2);
+            } else {
+                float x;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(a));
+                if (u & 1) f0 = __fmaf_rn(x, x, f0); else f2 = __fmaf_rn(x, x, f2);
+            }
+        }
+    }
+    const long long t1 = clock64();
+    if (f0 + f1 + f2 + f3 == 0.12345f) out[0] = 1.f;
+    __shared__ unsigned long long tmin, tmax;
+    if (threadIdx.x == 0) { tmin = ~0ull; tmax = 0ull; }
+    __syncthreads();
+    if (lane == 0) { atomicMin(&tmin, (unsigned long long)t0); atomicMax(&tmax, (unsigned long long)t1); }
+    __syncthreads();
+    if (threadIdx.x == 0) cyc[blockIdx.x] = (long long)(tmax - tmin);
+}
+
+template <int WIDTH, int PAT>
+static void run_lds(const char* name) {
+    auto kern = k_lds<WIDTH, PAT>;
+    const size_t smem = 48 * 1024;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int iters = 2000;
+    for (int rep = 0; rep < 2; rep++) kern<<<g_sms, 256, smem>>>(g_out, g_cyc, iters, (int)(smem / 4));
+    cudaDeviceSynchronize();
+    static long long h[4096];
+    cudaMemcpy(h, g_cyc, sizeof(long long) * g_sms, cudaMemcpyDeviceToHost);
+    double sum = 0;
+    for (int i = 0; i < g_sms; i++) sum += (double)h[i];
+    printf("{\"name\": \"%s\", \"sm_cycles_per_warp_load\": %.3f}\n", name, sum / g_sms / ((double)iters * 16 * 8));
+    fflush(stdout);
+}
+
+template <typename K>
+static void run(const char* name, K kern, int threads, int ctas_per_sm, size_t smem_bytes, int smem_floats, int nsteps,
+                double pipe_cycles_per_warp_step, double units_per_step, const char* unit) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem_bytes);
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, kern);
+    const int grid = g_sms * ctas_per_sm;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float ms = 0;
+    for (int rep = 0; rep < 2; rep++) {
+        cudaEventRecord(e0);
+        kern<<<grid, threads, smem_bytes>>>(g_out, g_cyc, nsteps, smem_floats);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+    }
+    cudaError_t err = cudaGetLastError();
+    static long long h[4096];
+    cudaMemcpy(h, g_cyc, sizeof(long long) * grid, cudaMemcpyDeviceToHost);
+    double sum = 0;
+    for (int i = 0; i < grid; i++) sum += (double)h[i];
+    const double cyc_cta = sum / grid;                         // cycles one CTA needed (its CTAs-per-SM neighbours ran concurrently)
+    const int warps_per_smsp = threads / 32 * ctas_per_sm / 4;
+    const double cyc_per_warp_step = cyc_cta / nsteps / warps_per_smsp;   // SMSP cycles per warp-step
+    printf("{\"name\": \"%s\", \"regs\": %d, \"occ\": %d, \"ctas_per_sm\": %d, \"warps_per_smsp\": %d, \"ms\": %.3f, \"cyc_per_cta_step\": %.1f, "
+           "\"smsp_cyc_per_warp_step\": %.2f, \"fma_pipe_util\": %.3f, \"%s_per_clk_per_sm\": %.2f, \"err\": \"%s\"}\n",
+           name, fa.numRegs, occ, ctas_per_sm, warps_per_smsp, ms, cyc_cta / nsteps, cyc_per_warp_step,
+           pipe_cycles_per_warp_step / cyc_per_warp_step, unit, units_per_step * (threads / 32) * ctas_per_sm / (cyc_cta / nsteps),
+           err == cudaSuccess ? "" : cudaGetErrorString(err));
+    fflush(stdout);
+}
+
+int main(int argc, char** argv) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaMalloc(&g_out, 64);
+    cudaMalloc(&g_cyc, sizeof(long long) * 4096);
+    const int HS = 200;            // H steps (32 columns each, 33 taps)
+    const int VS = 2000;           // V steps (4 input rows each)
+    const int sel = argc > 1 ? atoi(argv[1]) : 0;
+#define RUN_H(F, MB, CPS) run("h_flags" #F "_minb" #MB "_cps" #CPS, k_h<F, MB>, 128, CPS, (CPS > 3 ? 49152 : 65536), (CPS > 3 ? 12288 : 16384), HS, 33.0 * 64, 33.0, "warptaps")
+    constexpr int VST = 8 * 4 * 32 + 8 * 96 * 4 + 4 * 32 * 68;
+#define RUN_V(F, NWP, MB, CPS, NST) run("v_flags" #F "_nw" #NWP "_minb" #MB "_cps" #CPS, k_v<F, NWP, MB>, NWP * 32, CPS, (size_t)NST * VST * 4, NST * VST, VS, 512.0, 1.0, "warpsteps")
+    if (sel == 0) {
+    RUN_H(15, 2, 2);
+    RUN_H(31, 2, 2);
+    RUN_H(15, 3, 3);
+    RUN_H(31, 3, 3);
+    }
+    return 0;
+}
