@@ -137,6 +137,45 @@ ASW_API int asw_disparity_band_device(asw_ctx* ctx, const uint8_t* d_left_rgba, 
                                       int y0, int y1, const asw_params* prm, uint8_t* d_disp_rgba, uint8_t* d_disp_d,
                                       float* d_conf, asw_timing* timing);
 
+/* Row-band variant with a per-iteration halo exchange (alternative (i)): the band keeps only `radius`
+ * halo rows and every iteration aggregates exactly the rows [y0, y1) -- no halo rows are recomputed.  After the
+ * horizontal pass of every iteration but the last, `exchange` is called with DEVICE pointers into the band's cost
+ * volume: `top_send` / `bottom_send` are this band's first / last `radius` rows (`bytes` each, contiguous), to be
+ * delivered to the `bottom_recv` of the band above / the `top_recv` of the band below; `top_recv` / `bottom_recv` is
+ * where the neighbours' rows belong.  Pointers towards a frame border are NULL.  The work of the iteration has been
+ * ENQUEUED on asw_stream(ctx) when the callback runs: it must order its transfers after that work and must not return
+ * before this band's receive buffers are complete and its send buffers may be overwritten (every band's next
+ * horizontal pass rewrites its send rows).  Returns non-zero to abort.  The result is bit-identical to the same rows of
+ * asw_disparity_device: the reference itself has no multi-device split (main.cpp:158-172 visits devices one by one). */
+typedef int (*asw_halo_fn)(void* user, int iteration, void* top_send, void* bottom_send, void* top_recv, void* bottom_recv,
+                           size_t bytes);
+ASW_API int asw_disparity_band_exchange_device(asw_ctx* ctx, const uint8_t* d_left_rgba, const uint8_t* d_right_rgba, int W,
+                                               int H, int y0, int y1, const asw_params* prm, uint8_t* d_disp_rgba,
+                                               uint8_t* d_disp_d, float* d_conf, asw_halo_fn exchange, void* user,
+                                               asw_timing* timing);
+
+/* ---- one frame on several GPUs of one process -----------------------------------------------------
+ * Replaces the reference's device loop (main.cpp:119-130,158-172, which runs the WHOLE job on every device in turn)
+ * by a split of one frame: row bands, one band per listed CUDA device, `radius` boundary rows pulled from the
+ * neighbouring bands' volumes over NVLink between iterations (cudaMemcpyPeerAsync; no rows are recomputed).  Host
+ * buffers in and out as asw_disparity; the result is bit-identical to asw_disparity on one device. */
+typedef struct asw_multi asw_multi;
+typedef struct asw_multi_timing {
+    int devices;
+    float upload_ms;                /* host wall clock: image rows to every device */
+    float compute_ms;               /* host wall clock: first launch to the slowest band's last kernel */
+    float download_ms;              /* host wall clock: bands of the result into the caller's buffers */
+    float total_ms;
+    float slowest_band_device_ms;   /* CUDA-event time of the slowest band (includes its waits for the neighbours) */
+} asw_multi_timing;
+ASW_API int asw_multi_create(asw_multi** out, const int* devices, int n_devices);
+ASW_API int asw_multi_destroy(asw_multi* m);
+ASW_API int asw_multi_count(asw_multi* m);
+ASW_API const char* asw_multi_last_error(asw_multi* m);
+ASW_API int asw_multi_disparity(asw_multi* m, const uint8_t* left_rgba, const uint8_t* right_rgba, int W, int H,
+                                const asw_params* prm, uint8_t* disp_rgba, uint8_t* disp_d, float* conf,
+                                asw_multi_timing* timing);
+
 /* Disparity-shard variant for multi-GPU sharding without halo work: aggregates only the disparities [d0, d1)
  * (d0 a multiple of 64) for output rows [y0, y1) and returns the shard's partial winner-take-all result per pixel:
  * smallest and second smallest aggregated cost and the GLOBAL index of the smallest ((y1-y0)*W each).  Planes of the

@@ -24,7 +24,9 @@ ASW_OK, ASW_ERR_INVALID, ASW_ERR_CUDA, ASW_ERR_NOMEM, ASW_ERR_UNSUPPORTED = rang
 # every symbol include/asw_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
     "asw_version", "asw_strerror", "asw_create", "asw_destroy", "asw_last_error", "asw_stream", "asw_sync",
-    "asw_device_info", "asw_params_default", "asw_disparity", "asw_disparity_device", "asw_disparity_band_device", "asw_disparity_shard_device", "asw_merge_shards",
+    "asw_device_info", "asw_params_default", "asw_disparity", "asw_disparity_device", "asw_disparity_band_device", "asw_disparity_band_exchange_device",
+    "asw_multi_create", "asw_multi_destroy", "asw_multi_count", "asw_multi_last_error", "asw_multi_disparity",
+    "asw_disparity_shard_device", "asw_merge_shards",
     "asw_set_keep_volume", "asw_final_volume", "asw_Aggr", "asw_vSupport", "asw_hSupport", "asw_vCostAggregation",
     "asw_hCostAggregation", "asw_WTA", "asw_Constistency", "asw_ref_v", "asw_ref_h", "asw_WTA_REF", "asw_Median", "asw_stereo",
     "asw_cross_params_default", "asw_Median_grid", "asw_Cross", "asw_Aggregation", "asw_Integral_h", "asw_Integral_v", "asw_Oii_hcross",
@@ -52,6 +54,18 @@ class CTiming(C.Structure):
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class CMultiTiming(C.Structure):
+    _fields_ = [("devices", C.c_int), ("upload_ms", C.c_float), ("compute_ms", C.c_float), ("download_ms", C.c_float),
+                ("total_ms", C.c_float), ("slowest_band_device_ms", C.c_float)]
+
+    def as_dict(self) -> dict:
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+# asw_halo_fn: int (*)(void* user, int iteration, void* top_send, void* bottom_send, void* top_recv, void* bottom_recv, size_t bytes)
+HALO_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)
 
 
 class CTailTiming(C.Structure):
@@ -130,6 +144,13 @@ def load_library() -> C.CDLL:
     lib.asw_disparity.argtypes = [vp, u8p, u8p, C.c_int, C.c_int, pp, u8p, u8p, f32p, tp]
     lib.asw_disparity_device.argtypes = [vp, u8p, u8p, C.c_int, C.c_int, pp, u8p, u8p, f32p, tp]
     lib.asw_disparity_band_device.argtypes = [vp, u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, pp, u8p, u8p, f32p, tp]
+    lib.asw_disparity_band_exchange_device.argtypes = [vp, u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, pp, u8p, u8p, f32p, HALO_FN, vp, tp]
+    lib.asw_multi_create.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.c_int]
+    lib.asw_multi_destroy.argtypes = [vp]
+    lib.asw_multi_count.argtypes = [vp]
+    lib.asw_multi_last_error.restype = C.c_char_p
+    lib.asw_multi_last_error.argtypes = [vp]
+    lib.asw_multi_disparity.argtypes = [vp, u8p, u8p, C.c_int, C.c_int, pp, u8p, u8p, f32p, C.POINTER(CMultiTiming)]
     lib.asw_disparity_shard_device.argtypes = [vp, u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, pp, f32p, f32p, vp, tp]
     lib.asw_merge_shards.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, f32p, f32p, vp, u8p, u8p, f32p]
     lib.asw_set_keep_volume.argtypes = [vp, C.c_int]
@@ -319,6 +340,31 @@ class AswContext:
         self._check(st)
         return tm.as_dict() if tm is not None else None
 
+    def disparity_band_exchange(self, left_ptr: int, right_ptr: int, W: int, H: int, params: AswParams, band: tuple[int, int],
+                                rgba_ptr: int | None, d_ptr: int | None, conf_ptr: int | None, exchange, timing: bool = False):
+        """asw_disparity_band_exchange_device: rows band = (y0, y1) with a per-iteration halo exchange.
+        `exchange(iteration, top_send, bottom_send, top_recv, bottom_recv, nbytes)` receives device addresses (None towards
+        a frame border) and must have moved the rows when it returns (see include/asw_b200.h for the ordering contract)."""
+        err = []
+
+        def _cb(_user, it, ts, bs, tr, br, nbytes):
+            try:
+                exchange(it, ts, bs, tr, br, nbytes)
+                return 0
+            except Exception as e:      # an exception must not cross the C frames
+                err.append(e)
+                return 1
+
+        cb = HALO_FN(_cb)
+        tm = CTiming() if timing else None
+        p = params.c()
+        st = self.lib.asw_disparity_band_exchange_device(self.h, left_ptr, right_ptr, W, H, band[0], band[1], C.byref(p), rgba_ptr, d_ptr,
+                                                         conf_ptr, cb, None, C.byref(tm) if tm is not None else None)
+        if err:
+            raise err[0]
+        self._check(st)
+        return tm.as_dict() if tm is not None else None
+
     def stereo(self, left: np.ndarray, right: np.ndarray, params: AswParams | None = None, refine_iters: int = 6) -> dict:
         """The whole ASW method (asw_stereo): final disparity image + the two consistency images."""
         params = params or AswParams()
@@ -420,3 +466,49 @@ class AswContext:
         p = params.c()
         self._check(self.lib.asw_WTA(self.h, W, H, C.byref(p), cost, output, d_est_reference, d_est_target, output_target,
                                      confidence_reference, confidence_target))
+
+
+class AswMulti:
+    """One frame on several GPUs of this process (asw_multi_*): row bands, neighbour rows pulled over NVLink between
+    iterations.  Host buffers in and out, bit-identical to AswContext.disparity on one GPU."""
+
+    def __init__(self, devices):
+        self.lib = load_library()
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        st = self.lib.asw_multi_create(C.byref(h), devs, len(devices))
+        if st != ASW_OK:
+            raise AswError(st, f"asw_multi_create({list(devices)}) failed: {self.lib.asw_strerror(st).decode()}")
+        self.h, self.devices = h, list(devices)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.asw_multi_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def disparity(self, left: np.ndarray, right: np.ndarray, params: AswParams | None = None, want_conf: bool = True) -> dict:
+        params = params or AswParams()
+        left, right = _rgba(left), _rgba(right)
+        H, W, _ = left.shape
+        out = {"disp_rgba": np.empty((H, W, 4), np.uint8),
+               "disp_d": np.empty((H, W), np.uint8) if params.ndisp <= 256 else None,
+               "conf": np.empty((H, W), np.float32) if want_conf else None}
+        tm, p = CMultiTiming(), params.c()
+        st = self.lib.asw_multi_disparity(self.h, left.ctypes.data, right.ctypes.data, W, H, C.byref(p), _host_ptr(out["disp_rgba"]),
+                                          _host_ptr(out["disp_d"]), _host_ptr(out["conf"]), C.byref(tm))
+        if st != ASW_OK:
+            raise AswError(st, f"{self.lib.asw_strerror(st).decode()}: {self.lib.asw_multi_last_error(self.h).decode()}")
+        out["timing"] = tm.as_dict()
+        return out

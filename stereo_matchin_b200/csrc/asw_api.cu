@@ -199,16 +199,23 @@ struct Shard {            // disparity shard [d0, d1) of the problem and where i
     int* arg = nullptr;
 };
 
+struct HaloX {            // per-iteration halo exchange with the neighbouring row bands (asw_disparity_band_exchange_device)
+    asw_halo_fn fn = nullptr;
+    void* user = nullptr;
+};
+
 int run_band(asw_ctx* ctx, const uint8_t* dl, const uint8_t* dr, int W, int H, int y0, int y1, const asw_params* p,
-             uint8_t* d_rgba, uint8_t* d_d, float* d_conf, asw_timing* tm, const Shard* sh = nullptr) {
+             uint8_t* d_rgba, uint8_t* d_d, float* d_conf, asw_timing* tm, const Shard* sh = nullptr, const HaloX* hx = nullptr) {
     const int R = p->radius, T = 2 * R + 1, Dfull = p->ndisp, r = p->iterations;
     const int sd0 = sh ? sh->d0 : 0, sd1 = sh ? sh->d1 : Dfull;
     const int D = sd1 - sd0;                                   // disparities aggregated by this call
-    // rows whose values can influence rows [y0,y1): R rows per V pass (H passes stay in-row)
-    const int ya = max(0, y0 - r * R), yb = min(H, y1 + r * R);
+    // rows whose values can influence rows [y0,y1): R rows per V pass (H passes stay in-row).  With a halo exchange the
+    // band keeps only R halo rows and every iteration works on exactly [y0,y1): the neighbours' rows arrive between iterations.
+    const int ya = max(0, y0 - (hx ? R : r * R)), yb = min(H, y1 + (hx ? R : r * R));
     Band b{W, H, ya, yb - ya};
     const bool tma = ctx->family == 0 && tma_supported(R, Dfull);
     if (sh && !tma) return fail(ctx, ASW_ERR_UNSUPPORTED, "disparity shards need the TMA kernel family (radius 16, family 0)");
+    if (hx && !tma) return fail(ctx, ASW_ERR_UNSUPPORTED, "the halo exchange needs the TMA kernel family (radius 16, family 0)");
     const bool tiled = !tma && (ctx->family == 0 || ctx->family == 2) && tiled_supported(R);
     const TL tl = make_tl(b, Dfull, sd0, sd1);
     const int Dp = tma ? tma_padded_D(D) : tiled ? padded_D(D) : D;
@@ -245,13 +252,14 @@ int run_band(asw_ctx* ctx, const uint8_t* dl, const uint8_t* dr, int W, int H, i
         CUL(launch_unpack_v2(s, dr, W * H, (float4*)ctx->fimg_r.p));
         CUL(launch_raw_v2(s, fl, fr, tl, ya, yb, p->trunc, va));
         t.e_raw = t.et.mark();
-        CUL(launch_support_v2(s, true, false, fl, tl, ya, yb, p->gamma_c, p->gamma_p, vL));
-        CUL(launch_support_v2(s, false, false, fl, tl, ya, yb, p->gamma_c, p->gamma_p, hL));
-        CUL(launch_support_v2(s, true, true, fr, tl, ya, yb, p->gamma_c, p->gamma_p, vR));
-        CUL(launch_support_v2(s, false, true, fr, tl, ya, yb, p->gamma_c, p->gamma_p, hR));
+        const int ws0 = hx ? y0 : ya, ws1 = hx ? y1 : yb;     // rows that are ever aggregated: only they need weights
+        CUL(launch_support_v2(s, true, false, fl, tl, ws0, ws1, p->gamma_c, p->gamma_p, vL));
+        CUL(launch_support_v2(s, false, false, fl, tl, ws0, ws1, p->gamma_c, p->gamma_p, hL));
+        CUL(launch_support_v2(s, true, true, fr, tl, ws0, ws1, p->gamma_c, p->gamma_p, vR));
+        CUL(launch_support_v2(s, false, true, fr, tl, ws0, ws1, p->gamma_c, p->gamma_p, hR));
         t.prev = t.e_supp = t.et.mark();
         for (int it = 0; it < r; it++) {
-            const int ylo = max(ya, y0 - (r - 1 - it) * R), yhi = min(yb, y1 + (r - 1 - it) * R);
+            const int ylo = hx ? y0 : max(ya, y0 - (r - 1 - it) * R), yhi = hx ? y1 : min(yb, y1 + (r - 1 - it) * R);
             cudaEvent_t ev_main = nullptr;
             t.v_begin(it);
             if (t.pass_marks && t.et.on && t.et.n < asw_ctx::kMaxEvents) {   // an event between the main kernel and its fix-up / padding launches
@@ -263,6 +271,18 @@ int run_band(asw_ctx* ctx, const uint8_t* dl, const uint8_t* dr, int W, int H, i
             t.v_end(it);
             CUL(launch_hagg_v2(s, it == 0, tl, ylo, yhi, hL, hR, vb, den_h, va));
             t.h_end(it);
+            if (hx && it + 1 < r) {
+                // the next vertical pass reads R rows of each neighbour: hand out our boundary rows (volume rows are contiguous:
+                // Wv * Dp floats each) and where the neighbours' rows go; the callback moves them (NCCL, peer copies ...)
+                const size_t row = (size_t)tl.Wv * tl.Dp, bytes = sizeof(float) * row * R;
+                float* top_send = va + (size_t)(y0 - ya) * row;
+                float* bot_send = va + (size_t)(y1 - R - ya) * row;
+                float* top_recv = y0 > 0 ? va + (size_t)(y0 - R - ya) * row : nullptr;
+                float* bot_recv = y1 < H ? va + (size_t)(y1 - ya) * row : nullptr;
+                const int hs = hx->fn(hx->user, it, y0 > 0 ? top_send : nullptr, y1 < H ? bot_send : nullptr, top_recv, bot_recv, bytes);
+                if (hs) return fail(ctx, ASW_ERR_CUDA, "halo exchange callback failed");
+                t.prev = t.et.mark();                          // the exchange counts towards agg_total_ms, not towards the next V pass
+            }
         }
         t.e_agg = t.et.mark();
         CUL(launch_wta_v2(s, tl, y0, y1, y0, Dfull, va, d_rgba, d_d, d_conf, sh ? sh->min1 : nullptr, sh ? sh->min2 : nullptr, sh ? sh->arg : nullptr));
@@ -443,6 +463,26 @@ int asw_disparity_band_device(asw_ctx* ctx, const uint8_t* dl, const uint8_t* dr
     if (prm->ndisp > 256 && d_d) return fail(ctx, ASW_ERR_UNSUPPORTED, "disp_d is uint8: ndisp <= 256 required");
     CU(cudaSetDevice(ctx->device));
     return run_band(ctx, dl, dr, W, H, y0, y1, prm, d_rgba, d_d, d_conf, tm);
+}
+
+int asw_disparity_band_exchange_device(asw_ctx* ctx, const uint8_t* dl, const uint8_t* dr, int W, int H, int y0, int y1,
+                                       const asw_params* prm, uint8_t* d_rgba, uint8_t* d_d, float* d_conf, asw_halo_fn exchange,
+                                       void* user, asw_timing* tm) {
+    int st = check_params(ctx, W, H, prm);
+    if (st) return st;
+    if (!dl || !dr) return fail(ctx, ASW_ERR_INVALID, "image pointer is NULL");
+    if (!exchange) return fail(ctx, ASW_ERR_INVALID, "exchange callback is NULL");
+    if (y0 < 0 || y1 > H || y0 >= y1) return fail(ctx, ASW_ERR_INVALID, "band must satisfy 0 <= y0 < y1 <= H");
+    if ((y0 > 0 || y1 < H) && y1 - y0 < prm->radius) return fail(ctx, ASW_ERR_INVALID, "a band with neighbours needs at least `radius` rows");
+    if (prm->ndisp > 256 && d_d) return fail(ctx, ASW_ERR_UNSUPPORTED, "disp_d is uint8: ndisp <= 256 required");
+    CU(cudaSetDevice(ctx->device));
+    HaloX hx;
+    hx.fn = exchange; hx.user = user;
+    const int keep = ctx->keep_volume;
+    ctx->keep_volume = 0;
+    st = run_band(ctx, dl, dr, W, H, y0, y1, prm, d_rgba, d_d, d_conf, tm, nullptr, &hx);
+    ctx->keep_volume = keep;
+    return st;
 }
 
 int asw_disparity_shard_device(asw_ctx* ctx, const uint8_t* dl, const uint8_t* dr, int W, int H, int y0, int y1, int d0, int d1,

@@ -241,3 +241,62 @@ def cuda_shard_fn(ctx, params) -> ShardFn:
         return m1.cpu().numpy(), m2.cpu().numpy(), a.cpu().numpy()
 
     return fn
+
+
+# ---- row bands with a per-iteration halo exchange (alternative (i)) -------------------------------------
+# A vertical pass reaches R rows, so instead of carrying r*R recomputed halo rows a band can carry R rows and fetch its
+# neighbours' boundary rows between two iterations: no row is aggregated twice, the price is one neighbour exchange per
+# iteration (R * W * D * 4 bytes each way: 63 MB at 4K x 256, ~90 us over NVLink).  This is the one real exchange step of
+# the row-band sharding; everything else stays an all-gather of results.
+
+def halo_exchange(top_send, bottom_send, top_recv, bottom_recv, rank: int, world: int, group=None):
+    """Neighbour exchange of boundary rows between row bands (rank r owns band r; band r-1 lies above band r).
+    Arguments are torch tensors (or None towards a frame border): this rank's first / last rows to hand out, and
+    where the rows of the band above / below belong.  Works on NCCL (device tensors) and gloo (CPU tensors)."""
+    import torch.distributed as dist
+
+    if world == 1:
+        return
+    ops = []
+    if rank > 0:
+        ops.append(dist.P2POp(dist.isend, top_send, rank - 1, group))
+        ops.append(dist.P2POp(dist.irecv, top_recv, rank - 1, group))
+    if rank + 1 < world:
+        ops.append(dist.P2POp(dist.isend, bottom_send, rank + 1, group))
+        ops.append(dist.P2POp(dist.irecv, bottom_recv, rank + 1, group))
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+
+
+class _DevView:
+    """Zero-copy view of raw device memory for torch (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+def cuda_exchange_fn(ctx, rank: int, world: int, group=None, device=None):
+    """The product's exchange callback for AswContext.disparity_band_exchange: the library hands out device addresses into
+    its cost volume, NCCL send/recv moves the rows.  The library's stream is drained first (the rows of the iteration are
+    final), the NCCL work is drained before returning (the next vertical pass reads the received rows)."""
+    import torch
+
+    def fn(_it, top_send, bottom_send, top_recv, bottom_recv, nbytes):
+        ctx.sync()
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        view = lambda p: None if not p else torch.as_tensor(_DevView(p, nbytes), device=dev)
+        halo_exchange(view(top_send), view(bottom_send), view(top_recv), view(bottom_recv), rank, world, group)
+        torch.cuda.current_stream(dev).synchronize()
+
+    return fn
+
+
+def disparity_row_exchange_cuda(ctx, d_left: int, d_right: int, W: int, H: int, params, rank: int, world: int, out_band,
+                                group=None, timing: bool = False):
+    """This rank's band of one frame with halo exchange (device pointers of the FULL images in, `out_band` = torch uint8
+    tensor (rows, W) on this rank's GPU out).  Returns the library's timing dict if asked.  Bands: row_bands(H, world)."""
+    y0, y1 = row_bands(H, world)[rank]
+    if world == 1:
+        return ctx.disparity_raw(d_left, d_right, W, H, params, None, out_band.data_ptr(), None, timing=timing)
+    return ctx.disparity_band_exchange(d_left, d_right, W, H, params, (y0, y1), None, out_band.data_ptr(), None,
+                                       cuda_exchange_fn(ctx, rank, world, group), timing=timing)

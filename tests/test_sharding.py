@@ -55,6 +55,38 @@ def _oracle_shard(left, right, band, dshard, D=128, r=1):
     return _two_min_scan(res["cost"][d0:d1, y0 - ya:y1 - ya], d0)
 
 
+def _oracle_band_exchange(left, right, rank, world, D=24, r=3, R=16):
+    """CPU statement of asw_disparity_band_exchange_device: this rank keeps R halo rows of the cost volume, aggregates
+    exactly its own rows every iteration (oracle operators on the local rows: their clamping only touches halo rows, which
+    are discarded) and swaps boundary rows with its neighbours through sharding.halo_exchange between iterations."""
+    import torch
+    from oracle import asw_oracle as O
+    from stereo_matchin_b200.sharding import row_bands, halo_exchange
+    H = left.shape[0]
+    y0, y1 = row_bands(H, world)[rank]
+    ya, yb = max(0, y0 - R), min(H, y1 + R)
+    L, Rr = np.ascontiguousarray(left[ya:yb]), np.ascontiguousarray(right[ya:yb])
+    a, b = y0 - ya, y1 - ya                                      # own rows inside the local arrays
+    cost = np.ascontiguousarray(O.asw_aggr(L, Rr, D))             # (D, rows, W): raw cost needs no exchange
+    vl, vr = O.asw_support(L, True), O.asw_support(Rr, True)
+    hl, hr = O.asw_support(L, False), O.asw_support(Rr, False)
+    for it in range(r):
+        h = O.asw_hcost_aggregation(hl, hr, O.asw_vcost_aggregation(vl, vr, cost, use_fma=True)[0], use_fma=True)
+        cost[:, a:b] = h[:, a:b]                                 # only the own rows are valid (and needed)
+        if it + 1 < r:
+            # volume rows are (D, W) slabs here; the exchange buffers are contiguous copies
+            ts = torch.from_numpy(np.ascontiguousarray(cost[:, a:a + R])) if rank > 0 else None
+            bs = torch.from_numpy(np.ascontiguousarray(cost[:, b - R:b])) if rank + 1 < world else None
+            tr = torch.empty_like(ts) if ts is not None else None
+            br = torch.empty_like(bs) if bs is not None else None
+            halo_exchange(ts, bs, tr, br, rank, world)
+            if tr is not None:
+                cost[:, a - R:a] = tr.numpy()
+            if br is not None:
+                cost[:, b:b + R] = br.numpy()
+    return O.asw_wta(np.ascontiguousarray(cost[:, a:b]), right_view=False)["d_ref"].astype(np.uint8), cost[:, a:b].copy()
+
+
 def _worker(rank, world, port, mode, q):
     import torch.distributed as dist
     from oracle import asw_oracle as O
@@ -67,6 +99,12 @@ def _worker(rank, world, port, mode, q):
             L, R = crop_pair("teddy", 150, 100, 150, 64)
             arg, conf = sharding.disparity_2d_sharded(L, R, 128, rank, world, _oracle_shard, grid=(2, 2))
             q.put((rank, np.stack([arg.astype(np.float32), conf])))
+        elif mode == "exchange":
+            L, R = crop_pair("teddy", 60, 10, 96, 118)      # 118 rows: uneven bands, every band >= 16 rows
+            band, vol = _oracle_band_exchange(L, R, rank, world)
+            import torch
+            full = sharding.gather_bands(torch.from_numpy(band), L.shape[0], L.shape[1], rank, world)
+            q.put((rank, (full.numpy(), vol)))
         elif mode == "bands":
             L, R = crop_pair("teddy", 40, 0, 120, 151)      # 151 rows: uneven bands
             full = sharding.disparity_row_sharded(L, R, rank, world, _oracle_band)
@@ -107,6 +145,22 @@ def test_row_band_sharding_matches_single_process(world):
     ref = _oracle_band(L, R, 0, L.shape[0])
     for r in range(world):
         assert np.array_equal(out[r], ref), f"rank {r}: gathered map differs from the unsharded result"
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_halo_exchange_bands_match_single_process(world):
+    """Row bands with R exchanged halo rows per iteration (no recomputed halo): disparity map and the final cost volume of
+    every band are bit-identical to the unsharded oracle."""
+    from oracle import asw_oracle as O
+    from stereo_matchin_b200.sharding import row_bands
+    out = _run(world, "exchange")
+    L, R = crop_pair("teddy", 60, 10, 96, 118)
+    ref = O.asw_hot_path(L, R, O.OracleParams(ndisp=24, iterations=3), use_fma=True, want_cost=True)
+    for r in range(world):
+        full, vol = out[r]
+        y0, y1 = row_bands(L.shape[0], world)[r]
+        assert np.array_equal(full, ref["d_ref"].astype(np.uint8)), f"rank {r}: gathered map differs from the unsharded result"
+        assert np.array_equal(vol.view(np.uint32), ref["cost"][:, y0:y1].view(np.uint32)), f"rank {r}: cost volume of the band differs"
 
 
 def test_pair_sharding_gathers_every_map():
