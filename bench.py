@@ -11,8 +11,11 @@ thesis' own "disparities per second" metric, BASELINE.md).
   roofline  : dominant kernel (the slower of the V / H aggregation passes) vs the FP32 peak
   cpu_baseline : the CPU oracle (port of the reference kernels) on a bounded sample, rank 0, N=1
 Multi-GPU: pair sharding (each rank owns its pairs, weak scaling, no data-path collective;
-one all-gather of the uint8 disparity maps at the end of a step) -- or, with --workload cfg4,
-row-band sharding of one 4K frame with a shrinking halo (strong scaling).
+one all-gather of the uint8 disparity maps at the end of a step).  The strong-scaling configuration
+of BASELINE.json (one 3840x2160x256 frame split into row bands, `radius` halo rows exchanged between
+iterations over NCCL) is measured in every run as `also.cfg4_strong`, with an in-run check that the
+gathered map equals the one-GPU map; `--workload cfg4` makes it the headline instead.
+Both arms (`--impl ours` / `--impl reference`) print the same `metric`, `unit` and `config`.
 """
 from __future__ import annotations
 
@@ -37,6 +40,7 @@ WORKLOADS = {
     "cfg4": ("cfg4_3840x2160_d256", 1, "synthetic 3840x2160 pair, 256 disparities, row-band sharded"),
     "cfg5": ("cfg5_1280x720_d128", 4, "synthetic 1280x720 pairs, 128 disparities, pair sharded"),
 }
+METRIC = "Mpix*disp/s (ASW agg+WTA)"          # the same string in both arms: the driver pairs the arms by it
 T_TAPS = 33
 FP32_PEAK_FALLBACK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # SMs x lanes x 2 x sm_max_mhz (MEASURED_PEAKS.json)
 
@@ -106,6 +110,23 @@ def oracle_sample(L, R, D, r, rows):
             "seconds": dt}, res
 
 
+def make_config_dict(args, W, H, D, pairs_per_rank, sharding_desc, Dp):
+    """`config` of the JSON line: identical in both arms."""
+    _, _, desc = WORKLOADS[args.workload]
+    return {"workload": f"{args.workload}: {desc}", "W": W, "H": H, "ndisp": D, "radius": 16, "iterations": args.iterations,
+            "pairs_per_rank": pairs_per_rank, "sharding": sharding_desc,
+            "l2": "inputs larger than L2: every pass streams a %.2f GB cost volume" % (4.0 * W * H * Dp / 1e9),
+            "kernel_family": {0: "tma", 1: "basic", 2: "tiled"}[args.family],
+            "reference_sample": "the reference arm (--impl reference) and cpu_baseline time the CPU port on the top %d of %d rows "
+                                "of the same pair, all host threads" % (min(H, max(33, int(args.ref_rows))), H)}
+
+
+def default_sharding_desc(args, world):
+    if args.workload == "cfg4":
+        return "row bands, %d halo rows exchanged per iteration (NCCL send/recv), all-gather of bands" % 16
+    return "pairs (independent), all-gather of disparity maps"
+
+
 def run_reference_arm(args, rank):
     """--impl reference: the reference's CPU implementation of the path (OpenMP port of its kernels;
     the OpenCL original cannot run here) on all host threads, bounded sample per step."""
@@ -116,22 +137,167 @@ def run_reference_arm(args, rank):
     L, R, _, D = synth.make_config(cfg)
     H, W, _ = L.shape
     rows = max(33, min(H, int(args.ref_rows)))
+    warm = max(args.warmup, 3)                                   # the same warm-up count as our arm
     times = []
     info = None
-    for i in range(args.warmup_ref + args.steps):
+    for i in range(warm + args.steps):
         info, _ = oracle_sample(L, R, D, args.iterations, rows)
-        if i >= args.warmup_ref:
+        if i >= warm:
             times.append(info["seconds"])
     ms = float(np.mean(times)) * 1e3
     v = W * rows * D / (ms * 1e-3) / 1e6
-    line = {"impl": "reference", "metric": "Mpix*disp/s (ASW agg+WTA)", "value": v, "unit": "Mpix*disp/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup_ref, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {desc}", "W": W, "H": H, "ndisp": D, "iterations": args.iterations,
-                       "sample_rows": rows},
+    Dp = (D + 63) // 64 * 64
+    ppr = WORKLOADS[args.workload][1]
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "Mpix*disp/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong" if args.workload == "cfg4" else "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "timing": "host wall clock around the CPU port",
+            "config": make_config_dict(args, W, H, D, ppr, default_sharding_desc(args, args.gpus), Dp),
             "cpu_baseline": {"value": v, "unit": "Mpix*disp/s", "cores": info["cores"], "kind": "port", "sample": info["sample"]},
             "e2e": {"value": v, "unit": "Mpix*disp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def parity_block(ctx, api, r):
+    """north_star: aggregated costs within 1e-5 relative of the reference, disparity flips counted and reported.  The CUDA
+    path (FMA-contracted tap accumulation, bit-identical to oracle(use_fma=1)) against the OTHER arithmetic an OpenCL build
+    of the reference may legally use (separately rounded multiply and add, oracle(use_fma=0)), on BASELINE.json configs[1]'s
+    shape (450x375, 61 disparities, r iterations)."""
+    from oracle import asw_oracle as O
+    from stereo_matchin_b200 import synth
+    L, R, _, D = synth.make_config("cfg2_teddy_shape")
+    H, W, _ = L.shape
+    p = api.AswParams(ndisp=D, iterations=r)
+    ctx.set_keep_volume(True)
+    dl, dr = ctx.to_device(L), ctx.to_device(R)
+    od = ctx.alloc(W * H)
+    ctx.disparity_raw(dl.ptr, dr.ptr, W, H, p, None, od.ptr, None)
+    ctx.sync()
+    cost = np.empty((D, H, W), np.float32)
+    ctx._check(ctx.lib.asw_memcpy_d2h(ctx.h, cost.ctypes.data, ctx.final_volume_ptr(), cost.nbytes))
+    d_gpu = od.download((H, W), np.uint8)
+    ctx.set_keep_volume(False)
+    for b in (dl, dr, od):
+        b.free()
+    ref = O.asw_hot_path(L, R, O.OracleParams(ndisp=D, iterations=r), use_fma=False, want_cost=True)
+    fma = O.asw_hot_path(L, R, O.OracleParams(ndisp=D, iterations=r), use_fma=True, want_cost=True)
+    rel = np.abs(cost - ref["cost"]) / np.maximum(np.abs(ref["cost"]), 1e-30)
+    d_ref = ref["d_ref"].astype(np.int32)
+    flips = d_gpu.astype(np.int32) != d_ref
+    # a flip is a tie flip when the reference's own two best costs are within the tolerance of each other
+    srt = np.sort(ref["cost"], axis=0)
+    near_tie = (srt[1] - srt[0]) <= 1e-5 * np.abs(srt[1])
+    return {"workload": "cfg2 shape: synthetic 450x375, 61 disparities, r=%d" % r,
+            "against": "CPU oracle with separately rounded multiply/add (use_fma=0), the other arithmetic the reference's OpenCL build may use",
+            "cost_rel_err_max": float(rel.max()), "cost_rel_err_tolerance": 1e-5,
+            "tie_flips": int((flips & near_tie).sum()), "other_flips": int((flips & ~near_tie).sum()),
+            "tie_flip_pct": float(100.0 * flips.sum() / flips.size), "tie_flip_pct_limit": 0.1,
+            "bit_identical_to_fma_oracle": bool(np.array_equal(cost.view(np.uint32), fma["cost"].view(np.uint32))
+                                                and np.array_equal(d_gpu, fma["d_ref"].astype(np.uint8)))}
+
+
+def cfg4_strong_block(ctx, api, torch, dist, rank, world, r, steps=3):
+    """BASELINE.json configs[3]: ONE 3840x2160x256 frame on all ranks, row bands, `radius` halo rows exchanged over NCCL
+    between iterations, one all-gather of the uint8 bands.  Device-timed (CUDA events on the library's stream, max over
+    ranks); the gathered map is compared byte for byte with rank 0's own unsharded result in the same run."""
+    from stereo_matchin_b200 import sharding, synth
+    L, R, _, D = synth.make_config("cfg4_3840x2160_d256")
+    H, W, _ = L.shape
+    p = api.AswParams(ndisp=D, iterations=r)
+    dl, dr = torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda()
+    y0, y1 = sharding.row_bands(H, world)[rank]
+    band = torch.empty((y1 - y0, W), dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.ExternalStream(ctx.stream())
+    full = None
+
+    def step():
+        nonlocal full
+        sharding.disparity_row_exchange_cuda(ctx, dl.data_ptr(), dr.data_ptr(), W, H, p, rank, world, band)
+        if world > 1:
+            ctx.sync()
+            full = sharding.gather_bands(band, H, W, rank, world)
+
+    step()                                                    # warm-up: allocations, NCCL channels
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    times = []
+    for _ in range(steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        step()
+        e1.record(stream)
+        stream.synchronize()
+        torch.cuda.synchronize()
+        # the exchange callbacks synchronise with the host, so the frame time is the wall clock of the slowest rank;
+        # the event span on the library's stream is reported beside it
+        t = torch.tensor([(time.perf_counter() - t0) * 1e3, e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        times.append(t.tolist())
+    ms_wall = float(np.median([t[0] for t in times]))
+    ms_dev = float(np.median([t[1] for t in times]))
+    equals = True
+    if world > 1 and rank == 0:
+        one = torch.empty((H, W), dtype=torch.uint8, device="cuda")
+        ctx.disparity_raw(dl.data_ptr(), dr.data_ptr(), W, H, p, None, one.data_ptr(), None)
+        ctx.sync()
+        equals = bool(torch.equal(full, one))
+        del one
+    del dl, dr, band, full
+    torch.cuda.synchronize()
+    return {"workload": "cfg4: ONE synthetic 3840x2160 pair, 256 disparities, r=%d, strong scaling" % r, "n_gpus": world,
+            "sharding": "%d row bands; %d halo rows exchanged with each neighbour per iteration (NCCL send/recv, %.0f MB each way); "
+                        "no rows recomputed; one all-gather of uint8 bands" % (world, 16, 16 * (((W + 63) // 64) * 64 + 32) * 256 * 4 / 1e6),
+            "ms_per_frame": ms_wall, "ms_per_frame_device_events": ms_dev, "Mpix_disp_per_s": W * H * D / ms_wall / 1e3,
+            "halo_rows_recomputed_fraction": 0.0, "equals_1gpu": equals,
+            "equals_1gpu_how": "rank 0 runs the unsharded frame after the timed steps and compares all %d bytes" % (W * H) if world > 1
+                               else "N=1 is the unsharded frame",
+            "timing": "median of %d frames; wall clock from a barrier to the last rank's completed all-gather, max over ranks" % steps}
+
+
+def cfg5_batch_block(api, torch, dist, rank, local_rank, world, r, pairs_per_rank=8, rounds=2):
+    """BASELINE.json configs[4]: a batch of 1280x720x128 pairs, pair sharded.  Host buffers (pinned) in and out through
+    asw_disparity_async on two contexts per GPU that alternate between pairs, so the upload / download of one pair runs
+    under the kernels of the other.  A bounded sample of the 1024-pair batch; the full batch time is extrapolated."""
+    from stereo_matchin_b200 import synth
+    W, H, D, _ = synth.CONFIGS["cfg5_1280x720_d128"]
+    p = api.AswParams(ndisp=D, iterations=r)
+    pairs = [synth.make_config("cfg5_1280x720_d128", rank * pairs_per_rank + i)[:2] for i in range(pairs_per_rank)]
+    hin = [(torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()) for a, b in pairs]
+    hout = [torch.empty((H, W), dtype=torch.uint8).pin_memory() for _ in pairs]
+    ctxs = [api.AswContext(local_rank), api.AswContext(local_rank)]
+
+    def run_batch():
+        for i, ((a, b), o) in enumerate(zip(hin, hout)):
+            ctxs[i & 1].disparity_async(a.data_ptr(), b.data_ptr(), W, H, p, None, o.data_ptr(), None)
+        for c in ctxs:
+            c.sync()
+
+    run_batch()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(rounds):
+        run_batch()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    for c in ctxs:
+        c.close()
+    npairs = pairs_per_rank * rounds * world
+    return {"workload": "cfg5: batch of synthetic 1280x720 pairs, 128 disparities, r=%d, pair sharded" % r, "n_gpus": world,
+            "pairs_timed": npairs, "pairs_per_s": npairs / dt, "Mpix_disp_per_s": npairs * W * H * D / dt / 1e6,
+            "seconds_for_1024_pairs_extrapolated": 1024.0 / (npairs / dt),
+            "h2d_bytes_per_pair": 2 * W * H * 4, "d2h_bytes_per_pair": W * H,
+            "timing": "host wall clock over %d pairs per rank (%d distinct x %d rounds), pinned host buffers in and out, "
+                      "two asw contexts per GPU alternating (asw_disparity_async), max over ranks" % (pairs_per_rank * rounds, pairs_per_rank, rounds)}
 
 
 def main():
@@ -142,13 +308,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--iterations", type=int, default=7)
-    ap.add_argument("--grid", default="", help="cfg4: force the (row bands)x(disparity shards) grid, e.g. 4x2")
-    ap.add_argument("--bands-only", action="store_true", help="cfg4: shard by row bands only (default: row bands x disparity shards)")
     ap.add_argument("--family", type=int, default=0, help="0 = TMA-fed kernels (default), 1 = basic kernels, 2 = tiled kernels without TMA")
     ap.add_argument("--cpu-rows", type=int, default=400, help="rows of the pair the CPU baseline sample covers")
     ap.add_argument("--ref-rows", type=int, default=400)
-    ap.add_argument("--warmup-ref", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the also.* blocks (cfg2, parity, cfg4_strong, cfg5_batch)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -160,7 +324,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from stereo_matchin_b200 import api, synth
+    from stereo_matchin_b200 import api, sharding, synth
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback exists)")
@@ -172,27 +336,16 @@ def main():
     cfg, pairs_per_rank, desc = WORKLOADS[args.workload]
     W, H, D, _ = synth.CONFIGS[cfg]
     r = args.iterations
-    band_mode = args.workload == "cfg4"
+    band_mode = args.workload == "cfg4"                          # one frame on all ranks: row bands + halo exchange
     params = api.AswParams(ndisp=D, iterations=r)
     ctx = api.AswContext(local_rank)
     ctx.set_kernel_family(args.family)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
 
     # ---- inputs: pinned host copies and device-resident copies --------------------------------
-    dshard, grid = None, (world, 1)
     if band_mode:
-        from stereo_matchin_b200 import sharding
         pairs = [synth.make_config(cfg, 0)[:2]]                      # every rank holds the full frame
-        grid = sharding.shard_grid(world, D) if args.family == 0 and not args.bands_only else (world, 1)
-        if args.grid:
-            grid = tuple(int(v) for v in args.grid.lower().split("x"))
-            assert grid[0] * grid[1] == world, "--grid must multiply to the number of ranks"
-        if H % grid[0]:
-            grid = (world, 1)
-        if grid[1] > 1:     # 2-D grid: row bands x disparity shards (no halo work along d), ranks of a band are consecutive
-            band, dshard, _, _ = sharding.rank_shard(rank, world, H, D, grid)
-        else:
-            band = ((H * rank) // world, (H * (rank + 1)) // world)
+        band = sharding.row_bands(H, world)[rank]
         out_rows = band[1] - band[0]
     else:
         pairs = [synth.make_config(cfg, rank * pairs_per_rank + i)[:2] for i in range(pairs_per_rank)]
@@ -203,62 +356,35 @@ def main():
     dev_in = [(a.cuda(non_blocking=False), b.cuda(non_blocking=False)) for a, b in host_in]
     dev_d = [torch.empty((out_rows, W), dtype=torch.uint8, device="cuda") for _ in pairs]
     gather = torch.empty((world, len(pairs), out_rows, W), dtype=torch.uint8, device="cuda") if world > 1 and not band_mode else None
-    gather_band = torch.empty((H, W), dtype=torch.uint8, device="cuda") if world > 1 and band_mode else None
-    nd = grid[1]
-    if dshard is not None:  # partial WTA triples of this rank, the gathered triples of all ranks, this band's shards re-laid out
-        parts = torch.empty((3, out_rows, W), dtype=torch.float32, device="cuda")
-        allparts = torch.empty((world, 3, out_rows, W), dtype=torch.float32, device="cuda")
-        gather_band = torch.empty((world, out_rows, W), dtype=torch.uint8, device="cuda")
-    units_per_step_rank = W * out_rows * ((dshard[1] - dshard[0]) if dshard else D) * len(pairs)   # pix*disp this rank produces per step
+    units_per_step_rank = W * out_rows * D * len(pairs)           # pix*disp this rank produces per step
     torch.cuda.synchronize()
 
     stage_log = []   # per-stage CUDA-event times of every hot-path call made inside the timed region
 
-    def shard_step(timing):
-        """cfg4 on a 2-D grid: aggregate this rank's (band, disparity shard), all-gather the partial WTA triples (the one
-        real exchange step of this sharding: 12 B per pixel and rank), merge this band's shards, all-gather the bands."""
-        l, rr = dev_in[0]
-        tmr = ctx.disparity_shard_raw(l.data_ptr(), rr.data_ptr(), W, H, params, band, dshard, parts[0].data_ptr(), parts[1].data_ptr(),
-                                      parts[2].data_ptr(), timing=timing)
-        with torch.cuda.stream(stream):
-            dist.all_gather_into_tensor(allparts, parts)
-            b0 = (rank // nd) * nd
-            mine = allparts[b0:b0 + nd].permute(1, 0, 2, 3).contiguous()           # [3][shard][rows][W]
-            ctx.merge_shards(W, out_rows, D, nd, mine[0].data_ptr(), mine[1].data_ptr(), mine[2].data_ptr(), None, dev_d[0].data_ptr(), None)
-            dist.all_gather_into_tensor(gather_band, dev_d[0])                      # rank b*nd holds band b
-        return tmr
-
     def step_device():
-        if dshard is not None:
-            stage_log.append(shard_step(True))
+        if band_mode:
+            stage_log.append(sharding.disparity_row_exchange_cuda(ctx, dev_in[0][0].data_ptr(), dev_in[0][1].data_ptr(), W, H, params, rank,
+                                                                  world, dev_d[0], timing=True))
+            if world > 1:   # uneven bands are padded inside gather_bands
+                sharding.gather_bands(dev_d[0], H, W, rank, world)
             return
         for (l, rr), o in zip(dev_in, dev_d):
             # timing=True: the library brackets every kernel group with events on its own stream (and waits for
             # them at the end of the call, a ~20 us host gap per call that stays inside the timed region)
-            stage_log.append(ctx.disparity_raw(l.data_ptr(), rr.data_ptr(), W, H, params, None, o.data_ptr(), None, timing=True, band=band))
-        if world > 1:   # the single collective: all-gather of the uint8 disparity maps / bands
+            stage_log.append(ctx.disparity_raw(l.data_ptr(), rr.data_ptr(), W, H, params, None, o.data_ptr(), None, timing=True))
+        if world > 1:   # the single collective: all-gather of the uint8 disparity maps
             with torch.cuda.stream(stream):
-                if band_mode and H % world == 0:
-                    dist.all_gather_into_tensor(gather_band, dev_d[0])
-                elif not band_mode:
-                    dist.all_gather_into_tensor(gather, torch.stack(dev_d) if len(dev_d) > 1 else dev_d[0].unsqueeze(0))
+                dist.all_gather_into_tensor(gather, torch.stack(dev_d) if len(dev_d) > 1 else dev_d[0].unsqueeze(0))
 
     def step_host():
-        if dshard is not None:
-            with torch.cuda.stream(stream):
-                dev_in[0][0].copy_(host_in[0][0], non_blocking=True)
-                dev_in[0][1].copy_(host_in[0][1], non_blocking=True)
-            shard_step(False)
-            with torch.cuda.stream(stream):
-                host_d[0].copy_(dev_d[0], non_blocking=True)
-            stream.synchronize()
-            return
         for (l, rr), o, of in zip(host_in, host_d, host_full_d):
             if band_mode:   # upload, run the band on device pointers, download the band
                 with torch.cuda.stream(stream):
                     dev_in[0][0].copy_(l, non_blocking=True)
                     dev_in[0][1].copy_(rr, non_blocking=True)
-                    ctx.disparity_raw(dev_in[0][0].data_ptr(), dev_in[0][1].data_ptr(), W, H, params, None, dev_d[0].data_ptr(), None, band=band)
+                stream.synchronize()
+                sharding.disparity_row_exchange_cuda(ctx, dev_in[0][0].data_ptr(), dev_in[0][1].data_ptr(), W, H, params, rank, world, dev_d[0])
+                with torch.cuda.stream(stream):
                     o.copy_(dev_d[0], non_blocking=True)
                 stream.synchronize()
             else:           # the user-facing call: host buffers in, host buffers out, synchronous
@@ -281,8 +407,8 @@ def main():
         torch.cuda.synchronize()
         wall = (time.perf_counter() - t0) * 1e3
         ms = e0.elapsed_time(e1)
-        if fn is step_host and not band_mode:
-            ms = wall       # host entry point is synchronous per call: the wall clock is the honest number
+        if fn is step_host or band_mode:
+            ms = wall       # synchronous host entry point / host-synchronised halo exchange: the wall clock is the honest number
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -290,42 +416,47 @@ def main():
         return float(t.item())
 
     # ---- timed regions ---------------------------------------------------------------------------
+    warm = max(args.warmup, 3)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_dev = timed(step_device, args.steps, max(args.warmup, 3))
+    ms_dev = timed(step_device, args.steps, warm)
     clocks = sampler.stop() if rank == 0 else None
     timed_calls = stage_log[-args.steps * len(pairs):]           # the calls of the timed region (warm-up calls dropped)
     ms_host = timed(step_host, args.steps, 1)
 
-    total_units = units_per_step_rank
-    if world > 1:
+    total_units = float(W * H * D) if band_mode else float(units_per_step_rank)
+    if world > 1 and not band_mode:
         tu = torch.tensor([float(units_per_step_rank)], dtype=torch.float64, device="cuda")
         dist.all_reduce(tu)
         total_units = float(tu.item())
     value = total_units * args.steps / (ms_dev * 1e-3) / 1e6
     e2e_value = total_units * args.steps / (ms_host * 1e-3) / 1e6
 
-    # ---- per-stage timing of one instrumented step (outside the timed region) ----------------------
     tm = {k: float(np.mean([c[k] for c in timed_calls])) for k in timed_calls[0]}
     launches_per_pair = int(timed_calls[0]["kernel_launches"])
+
+    # ---- the other configurations of BASELINE.json, measured beside the headline (all ranks take part) ----------
+    also = {}
+    if not args.no_also and args.workload == "cfg3":
+        del dev_in, dev_d, gather                               # make room: the 4K frame needs 38 GB of scratch on one GPU
+        dev_in = dev_d = gather = None
+        torch.cuda.empty_cache()
+        also["cfg4_strong"] = cfg4_strong_block(ctx, api, torch, dist, rank, world, r)
+        also["cfg5_batch"] = cfg5_batch_block(api, torch, dist, rank, local_rank, world, r)
 
     if rank == 0:
         # roofline of the dominant kernel: F_alg of one pass = 4*T*W*rows*D, over its mean duration
         rows_mean = out_rows
-        if band_mode:   # halo rows computed per pass, averaged over the r iterations
-            rows_mean = float(np.mean([min(H, band[1] + (r - 1 - it) * 16) - max(0, band[0] - (r - 1 - it) * 16) for it in range(r)]))
-        D_rank = (dshard[1] - dshard[0]) if dshard else D             # disparities this rank aggregates
-        pass_flops = 4.0 * T_TAPS * W * rows_mean * D_rank
-        # V pass = main kernel + two small launches (diagonal fix-up, edge padding): the dominant KERNEL is the main one
+        pass_flops = 4.0 * T_TAPS * W * rows_mean * D
+        # V pass = main kernel + the edge padding launch: the dominant KERNEL is the main one
         v_ms, h_ms = tm["vagg_mean_ms"] - tm["vfix_mean_ms"], tm["hagg_mean_ms"]
-        tma = args.family == 0                                   # radius 16: the TMA-fed kernels (D padded to 128 internally)
+        tma = args.family == 0                                   # radius 16: the TMA-fed kernels (D padded to 64 internally)
         v_name = "k_vagg_v2 (asw_vCostAggregation; mean of its %d launches per frame)" % r if tma else "k_vagg_t (asw_vCostAggregation)"
         h_name = "k_hagg_split (asw_hCostAggregation)" if tma else "k_hagg_t (asw_hCostAggregation)"
         dom, dom_ms = (v_name, v_ms) if v_ms >= h_ms else (h_name, h_ms)
-        if v_ms >= h_ms and tma:
-            pass_flops *= (D - 1.5) / D                         # the fix-up launch produces 1.5 of the D outputs per pixel
-        peak, peak_src = FP32_PEAK_FALLBACK_TFLOPS, "computed: 148 SMs x 128 lanes x 2 x 1.965 GHz (MEASURED_PEAKS.json has no FP32 figure)"
+        peak = FP32_PEAK_FALLBACK_TFLOPS
+        peak_src = "computed: 148 SMs x 128 lanes x 2 x 1.965 GHz (MEASURED_PEAKS.json holds HBM GB/s and bf16 TFLOP/s, no FP32 figure)"
         ffma = None
         try:
             ub = C.CDLL(os.path.join(ROOT, "stereo_matchin_b200", "libasw_ubench.so"))
@@ -333,32 +464,39 @@ def main():
             ffma = {"ffma_tflops": ub.asw_ubench_ffma_tflops(0), "ffma2_tflops": ub.asw_ubench_ffma_tflops(1)}
         except Exception as e:  # measurement helper only
             ffma = {"error": str(e)}
+        peak_measured = max(ffma.get("ffma_tflops", 0.0), ffma.get("ffma2_tflops", 0.0)) if "error" not in ffma else None
         achieved = pass_flops / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
         peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
         hbm_peak = json.load(open(peaks_file)).get("hbm_gbs") if os.path.exists(peaks_file) else 6650.0
-        Dp = (D_rank + 63) // 64 * 64 if args.family == 0 else (D + 31) // 32 * 32
-        pass_bytes = 3.0 * 4 * W * rows_mean * Dp      # tiled kernels: read cost + read denominator + write cost
-        traffic, traffic_src = None, None                       # DRAM bytes per launch of that kernel, from the committed ncu --set full capture
-        tfiles = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_traffic.json")) if os.path.isdir(os.path.join(ROOT, "profiles")) else []
-        if tfiles and args.workload == "cfg3" and world == 1:
-            tj = json.load(open(os.path.join(ROOT, "profiles", tfiles[-1])))
+        Dp = (D + 63) // 64 * 64 if args.family == 0 else (D + 31) // 32 * 32
+        pass_bytes = 3.0 * 4 * W * rows_mean * Dp      # read cost + read denominator + write cost
+        traffic, traffic_src = None, None              # DRAM bytes per launch of that kernel, from the committed ncu --set full capture
+        pdir = os.path.join(ROOT, "profiles")
+        tfiles = sorted(f for f in os.listdir(pdir) if f.endswith("_traffic.json")) if os.path.isdir(pdir) else []
+        if tfiles and args.workload == "cfg3":         # every rank runs the same cfg3 launches: the per-launch traffic holds at any N
+            tj = json.load(open(os.path.join(pdir, tfiles[-1])))
             key = "k_vagg_v2" if v_ms >= h_ms else "k_hagg_split"
             if key in tj:
                 traffic, traffic_src = tj[key]["dram_bytes_per_launch"], "profiles/" + tfiles[-1]
+        whole = alg_flops(W, rows_mean, D, r) / (tm["total_ms"] * 1e-3) / 1e12
         roofline = {"bound": "fp32", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": pass_bytes,
                     "timing": "CUDA events on the library's stream around every launch group, mean over the timed region",
-                    "peak_source": peak_src, "measured_ffma_microbench": ffma,
-                    "whole_path_frac": alg_flops(W, rows_mean, D_rank, r) / (tm["total_ms"] * 1e-3) / 1e12 / peak,
+                    "peak_source": peak_src, "peak_measured": peak_measured,
+                    "peak_measured_source": "FP32 FMA microbenchmark run by this process on this GPU (libasw_ubench.so: dependent FFMA / FFMA2 chains, ILP 8, best of 5)",
+                    "frac_of_peak_measured": achieved / peak_measured if peak_measured else None,
+                    "measured_ffma_microbench": ffma,
+                    "whole_path_frac": whole / peak, "whole_path_frac_of_peak_measured": whole / peak_measured if peak_measured else None,
                     "v_pass_ms": v_ms, "h_pass_ms": h_ms,
+                    "other_pass": {"kernel": h_name if v_ms >= h_ms else v_name,
+                                   "frac": pass_flops / (min(v_ms, h_ms) * 1e-3) / 1e12 / peak if min(v_ms, h_ms) > 0 else None},
                     "hbm": {"algorithmic_gbs": pass_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0, "peak_gbs": hbm_peak,
                             "bytes_per_pass": pass_bytes}}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cpu, _ = oracle_sample(pairs[0][0], pairs[0][1], D, r, args.cpu_rows)
             cpu.pop("seconds", None)
-        also = None
-        if world == 1 and args.workload == "cfg3" and not args.no_cpu_baseline:
+        if world == 1 and args.workload == "cfg3" and not args.no_also:
             # BASELINE.json configs[1] (teddy / cones shape, 61 disparities) beside the headline: sub-millisecond kernels,
             # launch- and tail-dominated, so it is reported, not used for the roofline
             W2, H2, D2, _ = synth.CONFIGS["cfg2_teddy_shape"]
@@ -379,22 +517,21 @@ def main():
             for _ in range(10):
                 ctx.disparity_raw(L2.ctypes.data, R2.ctypes.data, W2, H2, p2, None, ho2.ctypes.data, None, host=True)
             host_ms = (time.perf_counter() - t0) * 1e3 / 10
-            also = {"cfg2": {"workload": "synthetic 450x375 pair, 61 disparities (BASELINE.json configs[1] shape), r=%d" % r,
-                             "ms_per_frame_device": dev_ms, "Mpix_disp_per_s": W2 * H2 * D2 / dev_ms / 1e3,
-                             "ms_per_frame_e2e_host_buffers": host_ms, "e2e_Mpix_disp_per_s": W2 * H2 * D2 / host_ms / 1e3,
-                             "timing": "wall clock around 20 back-to-back calls + stream sync (frames this small are launch-bound)"}}
+            also["cfg2"] = {"workload": "synthetic 450x375 pair, 61 disparities (BASELINE.json configs[1] shape), r=%d" % r,
+                            "ms_per_frame_device": dev_ms, "Mpix_disp_per_s": W2 * H2 * D2 / dev_ms / 1e3,
+                            "ms_per_frame_e2e_host_buffers": host_ms, "e2e_Mpix_disp_per_s": W2 * H2 * D2 / host_ms / 1e3,
+                            "timing": "wall clock around 20 back-to-back calls + stream sync (frames this small are launch-bound)"}
             del a2, b2, o2
+            also["parity"] = parity_block(ctx, api, r)
         npx_in = sum(a.numel() + b.numel() for a, b in host_in)
+        sharding_desc = default_sharding_desc(args, world)
         line = {
-            "metric": "Mpix*disp/s (ASW agg+WTA, device-timed)", "value": value, "unit": "Mpix*disp/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+            "metric": METRIC, "value": value, "unit": "Mpix*disp/s", "n_gpus": world,
+            "steps": args.steps, "warmup": warm, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
             "scaling": "strong" if band_mode else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {desc}", "W": W, "H": H, "ndisp": D, "radius": 16, "iterations": r,
-                       "pairs_per_rank": len(pairs), "sharding": (("%d row bands x %d disparity shards, all-gather of partial WTA triples + bands" % grid) if dshard is not None
-                                                                  else "row bands + shrinking halo, all-gather of bands" if band_mode
-                                                                  else "pairs (independent), all-gather of disparity maps"),
-                       "l2": "inputs larger than L2: every pass streams a %.2f GB cost volume" % (4.0 * W * H * Dp / 1e9),
-                       "kernel_family": {0: "tma", 1: "basic", 2: "tiled"}[args.family]},
+            "timing": "device: CUDA events on the library's stream, max over ranks" if not band_mode
+                      else "wall clock of the slowest rank (the halo exchange synchronises with the host)",
+            "config": make_config_dict(args, W, H, D, len(pairs), sharding_desc, Dp),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Mpix*disp/s", "h2d_bytes_per_step": int(npx_in), "d2h_bytes_per_step": int(W * out_rows * len(pairs)),
                     "ms_per_step": ms_host / args.steps},
@@ -402,14 +539,14 @@ def main():
             "stage_ms": {k: tm[k] for k in ("raw_ms", "supp_ms", "vagg_mean_ms", "vfix_mean_ms", "hagg_mean_ms", "agg_total_ms", "wta_ms", "total_ms")},
             "roofline": roofline,
             "cpu_baseline": cpu,
-            "also": also,
+            "also": also or None,
         }
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     # tensors allocated under the library's stream must be released before that stream is destroyed
-    del dev_in, dev_d, gather, gather_band, host_in, host_d, host_full_d
+    del dev_in, dev_d, gather, host_in, host_d, host_full_d
     torch.cuda.synchronize()
     torch.cuda.empty_cache()
     ctx.close()

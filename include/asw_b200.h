@@ -123,6 +123,14 @@ ASW_API void asw_params_default(asw_params* p);
 ASW_API int asw_disparity(asw_ctx* ctx, const uint8_t* left_rgba, const uint8_t* right_rgba, int W, int H,
                           const asw_params* prm, uint8_t* disp_rgba, uint8_t* disp_d, float* conf, asw_timing* timing);
 
+/* The same call without the final wait: upload, hot path and download are enqueued on the context's stream and the
+ * call returns; asw_sync(ctx) completes them.  Host buffers must be pinned (asw_host_alloc) for the copies to overlap
+ * other work, and must stay valid until the sync.  Two contexts on one device alternate between pairs of a batch
+ * (cfg5: 1024 pairs) so that the upload of pair i+1 runs under the kernels of pair i -- the reference uploads at buffer
+ * creation and reads back blocking (main.cpp:243-244,621), i.e. it has no such overlap. */
+ASW_API int asw_disparity_async(asw_ctx* ctx, const uint8_t* left_rgba, const uint8_t* right_rgba, int W, int H,
+                                const asw_params* prm, uint8_t* disp_rgba, uint8_t* disp_d, float* conf);
+
 /* Same with DEVICE pointers for inputs and outputs; asynchronous on the context's stream
  * unless `timing` is non-NULL (timing needs the events to complete). */
 ASW_API int asw_disparity_device(asw_ctx* ctx, const uint8_t* d_left_rgba, const uint8_t* d_right_rgba, int W, int H,

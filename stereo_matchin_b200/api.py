@@ -24,7 +24,7 @@ ASW_OK, ASW_ERR_INVALID, ASW_ERR_CUDA, ASW_ERR_NOMEM, ASW_ERR_UNSUPPORTED = rang
 # every symbol include/asw_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
     "asw_version", "asw_strerror", "asw_create", "asw_destroy", "asw_last_error", "asw_stream", "asw_sync",
-    "asw_device_info", "asw_params_default", "asw_disparity", "asw_disparity_device", "asw_disparity_band_device", "asw_disparity_band_exchange_device",
+    "asw_device_info", "asw_params_default", "asw_disparity", "asw_disparity_async", "asw_disparity_device", "asw_disparity_band_device", "asw_disparity_band_exchange_device",
     "asw_multi_create", "asw_multi_destroy", "asw_multi_count", "asw_multi_last_error", "asw_multi_disparity",
     "asw_disparity_shard_device", "asw_merge_shards",
     "asw_set_keep_volume", "asw_final_volume", "asw_Aggr", "asw_vSupport", "asw_hSupport", "asw_vCostAggregation",
@@ -142,6 +142,7 @@ def load_library() -> C.CDLL:
     lib.asw_params_default.argtypes = [pp]
     lib.asw_params_default.restype = None
     lib.asw_disparity.argtypes = [vp, u8p, u8p, C.c_int, C.c_int, pp, u8p, u8p, f32p, tp]
+    lib.asw_disparity_async.argtypes = [vp, u8p, u8p, C.c_int, C.c_int, pp, u8p, u8p, f32p]
     lib.asw_disparity_device.argtypes = [vp, u8p, u8p, C.c_int, C.c_int, pp, u8p, u8p, f32p, tp]
     lib.asw_disparity_band_device.argtypes = [vp, u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, pp, u8p, u8p, f32p, tp]
     lib.asw_disparity_band_exchange_device.argtypes = [vp, u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, pp, u8p, u8p, f32p, HALO_FN, vp, tp]
@@ -364,6 +365,12 @@ class AswContext:
             raise err[0]
         self._check(st)
         return tm.as_dict() if tm is not None else None
+
+    def disparity_async(self, left_ptr: int, right_ptr: int, W: int, H: int, params: AswParams, rgba_ptr: int | None,
+                        d_ptr: int | None, conf_ptr: int | None):
+        """asw_disparity_async: pinned HOST pointers; upload + hot path + download are enqueued, `sync()` completes them."""
+        p = params.c()
+        self._check(self.lib.asw_disparity_async(self.h, left_ptr, right_ptr, W, H, C.byref(p), rgba_ptr, d_ptr, conf_ptr))
 
     def stereo(self, left: np.ndarray, right: np.ndarray, params: AswParams | None = None, refine_iters: int = 6) -> dict:
         """The whole ASW method (asw_stereo): final disparity image + the two consistency images."""

@@ -521,8 +521,21 @@ int asw_disparity_device(asw_ctx* ctx, const uint8_t* dl, const uint8_t* dr, int
     return asw_disparity_band_device(ctx, dl, dr, W, H, 0, H, prm, d_rgba, d_d, d_conf, tm);
 }
 
+static int disparity_host(asw_ctx* ctx, const uint8_t* left, const uint8_t* right, int W, int H, const asw_params* prm,
+                          uint8_t* disp_rgba, uint8_t* disp_d, float* conf, asw_timing* tm, bool sync);
+
 int asw_disparity(asw_ctx* ctx, const uint8_t* left, const uint8_t* right, int W, int H, const asw_params* prm,
                   uint8_t* disp_rgba, uint8_t* disp_d, float* conf, asw_timing* tm) {
+    return disparity_host(ctx, left, right, W, H, prm, disp_rgba, disp_d, conf, tm, true);
+}
+
+int asw_disparity_async(asw_ctx* ctx, const uint8_t* left, const uint8_t* right, int W, int H, const asw_params* prm,
+                        uint8_t* disp_rgba, uint8_t* disp_d, float* conf) {
+    return disparity_host(ctx, left, right, W, H, prm, disp_rgba, disp_d, conf, nullptr, false);
+}
+
+static int disparity_host(asw_ctx* ctx, const uint8_t* left, const uint8_t* right, int W, int H, const asw_params* prm,
+                          uint8_t* disp_rgba, uint8_t* disp_d, float* conf, asw_timing* tm, bool sync) {
     int st = check_params(ctx, W, H, prm);
     if (st) return st;
     if (!left || !right) return fail(ctx, ASW_ERR_INVALID, "image pointer is NULL");
@@ -548,6 +561,7 @@ int asw_disparity(asw_ctx* ctx, const uint8_t* left, const uint8_t* right, int W
     if (disp_d) CU(cudaMemcpyAsync(disp_d, ctx->out_d.p, npx, cudaMemcpyDeviceToHost, ctx->stream));
     if (conf) CU(cudaMemcpyAsync(conf, ctx->out_conf.p, npx * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (tm) cudaEventRecord(e3, ctx->stream);
+    if (!sync) return ASW_OK;                                  // asw_disparity_async: the caller waits with asw_sync
     CU(cudaStreamSynchronize(ctx->stream));
     if (tm) {
         *tm = inner;
