@@ -247,10 +247,30 @@ def cfg4_strong_block(ctx, api, torch, dist, rank, world, r, steps=3):
         ctx.disparity_raw(dl.data_ptr(), dr.data_ptr(), W, H, p, None, one.data_ptr(), None)
         ctx.sync()
         equals = bool(torch.equal(full, one))
-        del one
+    one_process = None
+    if world > 1:
+        # the same frame through the C ABI's own multi-GPU entry (asw_multi_*): ONE process (rank 0) drives all `world` GPUs
+        # with a thread per band, copy-engine peer copies ordered by events, exchange hidden under the interior rows.  The
+        # other ranks wait at the barrier (their GPUs are idle), so the two measurements do not disturb each other.
+        if rank == 0:
+            d_one = one.cpu().numpy()
+            with api.AswMulti(list(range(world))) as m:
+                m.disparity(L, R, p, want_conf=False)
+                runs = [m.disparity(L, R, p, want_conf=False) for _ in range(steps)]
+            ms1 = float(np.median([x["timing"]["compute_ms"] for x in runs]))
+            one_process = {"how": "asw_multi_disparity from one process: %d band threads, cudaMemcpyPeerAsync of the halo rows on a communication "
+                                  "stream per band, ordered by CUDA events, under the interior rows of the iteration" % world,
+                           "ms_per_frame": ms1, "Mpix_disp_per_s": W * H * D / ms1 / 1e3,
+                           "upload_ms": float(np.median([x["timing"]["upload_ms"] for x in runs])),
+                           "download_ms": float(np.median([x["timing"]["download_ms"] for x in runs])),
+                           "equals_1gpu": bool(all(np.array_equal(x["disp_d"], d_one) for x in runs)),
+                           "timing": "host wall clock from the first launch to the slowest band's last kernel, median of %d frames" % steps}
+            del one
+        dist.barrier()
     del dl, dr, band, full
     torch.cuda.synchronize()
     return {"workload": "cfg4: ONE synthetic 3840x2160 pair, 256 disparities, r=%d, strong scaling" % r, "n_gpus": world,
+            "one_process": one_process,
             "sharding": "%d row bands; %d halo rows exchanged with each neighbour per iteration (NCCL send/recv, %.0f MB each way); "
                         "no rows recomputed; one all-gather of uint8 bands" % (world, 16, 16 * (((W + 63) // 64) * 64 + 32) * 256 * 4 / 1e6),
             "ms_per_frame": ms_wall, "ms_per_frame_device_events": ms_dev, "Mpix_disp_per_s": W * H * D / ms_wall / 1e3,

@@ -162,6 +162,23 @@ ASW_API int asw_disparity_band_exchange_device(asw_ctx* ctx, const uint8_t* d_le
                                                uint8_t* d_disp_d, float* d_conf, asw_halo_fn exchange, void* user,
                                                asw_timing* timing);
 
+/* The same exchange hidden under the computation: no call blocks the host.  Every iteration computes the `radius`
+ * boundary rows of its horizontal pass first, on a second stream beside the interior rows, and calls `begin` with the
+ * same pointers as above plus that stream (a cudaStream_t): the transfer must be ordered after the work enqueued on
+ * it and is left running.  The next iteration aggregates the interior rows of its vertical pass -- they read no halo
+ * row -- and then calls `end` with the main stream (asw_stream): the callback makes that stream wait for the transfer
+ * (receive buffers complete, send buffers free), after which the band's border rows are aggregated.  Neither callback
+ * may wait on the host for another band's GPU work. */
+typedef int (*asw_halo_begin_fn)(void* user, int iteration, void* top_send, void* bottom_send, void* top_recv, void* bottom_recv,
+                                 size_t bytes, void* boundary_stream);
+typedef int (*asw_halo_end_fn)(void* user, int iteration, void* main_stream);
+ASW_API int asw_disparity_band_exchange_async_device(asw_ctx* ctx, const uint8_t* d_left_rgba, const uint8_t* d_right_rgba,
+                                                     int W, int H, int y0, int y1, const asw_params* prm, uint8_t* d_disp_rgba,
+                                                     uint8_t* d_disp_d, float* d_conf, asw_halo_begin_fn begin,
+                                                     asw_halo_end_fn end, void* user, asw_timing* timing);
+/* the second stream of the context (boundary rows of the horizontal pass), as void* */
+ASW_API void* asw_side_stream(asw_ctx* ctx);
+
 /* ---- one frame on several GPUs of one process -----------------------------------------------------
  * Replaces the reference's device loop (main.cpp:119-130,158-172, which runs the WHOLE job on every device in turn)
  * by a split of one frame: row bands, one band per listed CUDA device, `radius` boundary rows pulled from the

@@ -16,7 +16,10 @@
 // --method both = cross + whole, the reference's full per-run sequence.  Columns of a method that did
 // not run are written as 0.
 //
-// Usage: stereo_matching [--pics pics.txt] [--root DIR] [--runs 10] [--device 0] [--ndisp 61]
+// --devices 0,1,2,3 (with --method hot) splits every frame into row bands over the listed GPUs (asw_multi_disparity:
+// the reference visits its devices one after the other with the whole job, main.cpp:158-172; here they share a frame).
+//
+// Usage: stereo_matching [--pics pics.txt] [--root DIR] [--runs 10] [--device 0 | --devices 0,1,...] [--ndisp 61]
 //                        [--iterations 7] [--method hot|whole|cross|both] [--refine 6] [--out-suffix _wta] [--log FILE]
 #include <cmath>
 #include <cstdio>
@@ -44,6 +47,7 @@ static const char* kHeader =
 int main(int argc, char** argv) {
     std::string pics = "pics.txt", root = ".", suffix = "_wta", log_name;
     int runs = 10, device = 0, refine = 6;   // k = 6, main.cpp:176
+    std::vector<int> devices;
     bool whole = false, hot = true, cross = false;
     asw_params prm;
     asw_params_default(&prm);
@@ -57,6 +61,16 @@ int main(int argc, char** argv) {
         else if (a == "--root") root = next("--root");
         else if (a == "--runs") runs = atoi(next("--runs"));
         else if (a == "--device") device = atoi(next("--device"));
+        else if (a == "--devices") {
+            std::string v = next("--devices");
+            for (size_t p = 0; p < v.size();) {
+                size_t q = v.find(',', p);
+                if (q == std::string::npos) q = v.size();
+                devices.push_back(atoi(v.substr(p, q - p).c_str()));
+                p = q + 1;
+            }
+            if (!devices.empty()) device = devices[0];
+        }
         else if (a == "--ndisp") prm.ndisp = atoi(next("--ndisp"));
         else if (a == "--iterations") prm.iterations = atoi(next("--iterations"));
         else if (a == "--refine") refine = atoi(next("--refine"));
@@ -90,6 +104,13 @@ int main(int argc, char** argv) {
     if (st != ASW_OK) {
         fprintf(stderr, "asw_create(device %d) failed: %s (a CUDA device is required)\n", device, asw_strerror(st));
         return 1;
+    }
+    asw_multi* multi = nullptr;
+    if (devices.size() > 1) {
+        if (!hot) { fprintf(stderr, "--devices needs --method hot (the frame split covers the hot path)\n"); asw_destroy(ctx); return 2; }
+        st = asw_multi_create(&multi, devices.data(), (int)devices.size());
+        if (st != ASW_OK) { fprintf(stderr, "asw_multi_create failed: %s\n", asw_strerror(st)); asw_destroy(ctx); return 1; }
+        printf("\t- %zu devices share every frame (row bands, halo rows exchanged between iterations)\n", devices.size());
     }
     char dev_name[256] = "";
     asw_device_info(ctx, nullptr, nullptr, nullptr, dev_name, sizeof dev_name);
@@ -147,10 +168,16 @@ int main(int argc, char** argv) {
             if (!whole && !hot) st = ASW_OK;
             else if (whole)
                 st = asw_stereo(ctx, imgL.pixel.data(), imgR.pixel.data(), (int)W, (int)H, &prm, refine, disp.data(), pre.data(), post.data(), &t, &tt);
-            else
+            else if (multi) {
+                asw_multi_timing mt;
+                st = asw_multi_disparity(multi, imgL.pixel.data(), imgR.pixel.data(), (int)W, (int)H, &prm, disp.data(), nullptr, nullptr, &mt);
+                t.agg_total_ms = t.total_ms = mt.compute_ms;   // the per-stage columns belong to one device; the frame total is what all share
+                t.h2d_ms = mt.upload_ms;
+                t.d2h_ms = mt.download_ms;
+            } else
                 st = asw_disparity(ctx, imgL.pixel.data(), imgR.pixel.data(), (int)W, (int)H, &prm, disp.data(), nullptr, nullptr, &t);
             if (st != ASW_OK) {
-                printf("ASW error executing hot path: %d (%s)\n", st, asw_last_error(ctx));   // ErCheck prints and continues
+                printf("ASW error executing hot path: %d (%s)\n", st, multi ? asw_multi_last_error(multi) : asw_last_error(ctx));   // ErCheck prints and continues
                 rc = 1;
                 continue;
             }
@@ -190,6 +217,7 @@ int main(int argc, char** argv) {
         }
     }
     fclose(to_file);
+    if (multi) asw_multi_destroy(multi);
     asw_destroy(ctx);
     return rc;
 }

@@ -24,7 +24,7 @@ ASW_OK, ASW_ERR_INVALID, ASW_ERR_CUDA, ASW_ERR_NOMEM, ASW_ERR_UNSUPPORTED = rang
 # every symbol include/asw_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
     "asw_version", "asw_strerror", "asw_create", "asw_destroy", "asw_last_error", "asw_stream", "asw_sync",
-    "asw_device_info", "asw_params_default", "asw_disparity", "asw_disparity_async", "asw_disparity_device", "asw_disparity_band_device", "asw_disparity_band_exchange_device",
+    "asw_device_info", "asw_params_default", "asw_disparity", "asw_disparity_async", "asw_disparity_device", "asw_disparity_band_device", "asw_disparity_band_exchange_device", "asw_disparity_band_exchange_async_device", "asw_side_stream",
     "asw_multi_create", "asw_multi_destroy", "asw_multi_count", "asw_multi_last_error", "asw_multi_disparity",
     "asw_disparity_shard_device", "asw_merge_shards",
     "asw_set_keep_volume", "asw_final_volume", "asw_Aggr", "asw_vSupport", "asw_hSupport", "asw_vCostAggregation",
@@ -66,6 +66,11 @@ class CMultiTiming(C.Structure):
 
 # asw_halo_fn: int (*)(void* user, int iteration, void* top_send, void* bottom_send, void* top_recv, void* bottom_recv, size_t bytes)
 HALO_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)
+
+
+# asw_halo_begin_fn / asw_halo_end_fn (asynchronous exchange hidden under the interior rows)
+HALO_BEGIN_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
+HALO_END_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p)
 
 
 class CTailTiming(C.Structure):
@@ -146,6 +151,10 @@ def load_library() -> C.CDLL:
     lib.asw_disparity_device.argtypes = [vp, u8p, u8p, C.c_int, C.c_int, pp, u8p, u8p, f32p, tp]
     lib.asw_disparity_band_device.argtypes = [vp, u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, pp, u8p, u8p, f32p, tp]
     lib.asw_disparity_band_exchange_device.argtypes = [vp, u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, pp, u8p, u8p, f32p, HALO_FN, vp, tp]
+    lib.asw_disparity_band_exchange_async_device.argtypes = [vp, u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, pp, u8p, u8p, f32p, HALO_BEGIN_FN,
+                                                             HALO_END_FN, vp, tp]
+    lib.asw_side_stream.restype = vp
+    lib.asw_side_stream.argtypes = [vp]
     lib.asw_multi_create.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.c_int]
     lib.asw_multi_destroy.argtypes = [vp]
     lib.asw_multi_count.argtypes = [vp]
@@ -361,6 +370,39 @@ class AswContext:
         p = params.c()
         st = self.lib.asw_disparity_band_exchange_device(self.h, left_ptr, right_ptr, W, H, band[0], band[1], C.byref(p), rgba_ptr, d_ptr,
                                                          conf_ptr, cb, None, C.byref(tm) if tm is not None else None)
+        if err:
+            raise err[0]
+        self._check(st)
+        return tm.as_dict() if tm is not None else None
+
+    def disparity_band_exchange_async(self, left_ptr: int, right_ptr: int, W: int, H: int, params: AswParams, band: tuple[int, int],
+                                      rgba_ptr: int | None, d_ptr: int | None, conf_ptr: int | None, begin, end, timing: bool = False):
+        """asw_disparity_band_exchange_async_device: `begin(iteration, top_send, bottom_send, top_recv, bottom_recv, nbytes,
+        boundary_stream)` starts the transfer (ordered after `boundary_stream`) and returns; `end(iteration, main_stream)` makes
+        `main_stream` wait for it.  Streams are raw cudaStream_t addresses.  Neither may block on another band's GPU work."""
+        err = []
+
+        def _b(_u, it, ts, bs, tr, br, nbytes, st):
+            try:
+                begin(it, ts, bs, tr, br, nbytes, st)
+                return 0
+            except Exception as e:
+                err.append(e)
+                return 1
+
+        def _e(_u, it, st):
+            try:
+                end(it, st)
+                return 0
+            except Exception as e:
+                err.append(e)
+                return 1
+
+        cb, ce = HALO_BEGIN_FN(_b), HALO_END_FN(_e)
+        tm = CTiming() if timing else None
+        p = params.c()
+        st = self.lib.asw_disparity_band_exchange_async_device(self.h, left_ptr, right_ptr, W, H, band[0], band[1], C.byref(p), rgba_ptr,
+                                                               d_ptr, conf_ptr, cb, ce, None, C.byref(tm) if tm is not None else None)
         if err:
             raise err[0]
         self._check(st)

@@ -32,6 +32,8 @@ struct Scratch {
 struct asw_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t side = nullptr;            // second stream: boundary rows of the horizontal pass under the interior rows (halo overlap)
+    cudaEvent_t ev_v = nullptr, ev_hb = nullptr;
     cudaDeviceProp prop{};
     std::string err;
     int family = 0;
@@ -199,8 +201,10 @@ struct Shard {            // disparity shard [d0, d1) of the problem and where i
     int* arg = nullptr;
 };
 
-struct HaloX {            // per-iteration halo exchange with the neighbouring row bands (asw_disparity_band_exchange_device)
-    asw_halo_fn fn = nullptr;
+struct HaloX {            // per-iteration halo exchange with the neighbouring row bands
+    asw_halo_fn fn = nullptr;               // host-synchronous exchange (asw_disparity_band_exchange_device)
+    asw_halo_begin_fn begin = nullptr;      // or: asynchronous exchange hidden under the interior rows (..._async_device)
+    asw_halo_end_fn end = nullptr;
     void* user = nullptr;
 };
 
@@ -258,6 +262,15 @@ int run_band(asw_ctx* ctx, const uint8_t* dl, const uint8_t* dr, int W, int H, i
         CUL(launch_support_v2(s, true, true, fr, tl, ws0, ws1, p->gamma_c, p->gamma_p, vR));
         CUL(launch_support_v2(s, false, true, fr, tl, ws0, ws1, p->gamma_c, p->gamma_p, hR));
         t.prev = t.e_supp = t.et.mark();
+        // Halo exchange hidden under the interior rows (hx->begin / hx->end): an iteration computes the boundary rows of
+        // its horizontal pass first (side stream, concurrently with the interior rows on the main stream), hands them to the
+        // transfer, and the next iteration aggregates the interior rows of its vertical pass (which read no halo row) before it
+        // waits for the neighbours' rows and finishes the R-row borders.  Split points of the vertical pass are multiples of
+        // 8 rows (its tiles), so no tile is shared between two launches.
+        const bool up = y0 > 0, down = y1 < H;                    // neighbours
+        const int vA = up ? min(y1, (y0 + R + 7) & ~7) : y0, vB = down ? max(vA, (y1 - R) & ~7) : y1;
+        const bool overlap = hx && hx->begin && (up || down) && vB - vA >= 8 && y1 - y0 >= 2 * R;
+        const size_t vrow = (size_t)tl.Wv * tl.Dp, hbytes = sizeof(float) * vrow * R;
         for (int it = 0; it < r; it++) {
             const int ylo = hx ? y0 : max(ya, y0 - (r - 1 - it) * R), yhi = hx ? y1 : min(yb, y1 + (r - 1 - it) * R);
             cudaEvent_t ev_main = nullptr;
@@ -266,22 +279,47 @@ int run_band(asw_ctx* ctx, const uint8_t* dl, const uint8_t* dr, int W, int H, i
                 t.ev_vmain[it] = t.et.n++;
                 ev_main = ctx->ev[t.ev_vmain[it]];
             }
-            CUL(launch_vagg_v2(s, it == 0, tl, ylo, yhi, vL, vR, va, den_v, vb, ev_main));
+            if (overlap && it > 0) {
+                CUL(launch_vagg_v2(s, false, tl, vA, vB, vL, vR, va, den_v, vb, ev_main));
+                if (hx->end(hx->user, it - 1, (void*)s)) return fail(ctx, ASW_ERR_CUDA, "halo exchange (end) callback failed");
+                if (vA > y0) { CUL(launch_vagg_v2(s, false, tl, y0, vA, vL, vR, va, den_v, vb)); ctx->launches += 2; }
+                if (y1 > vB) { CUL(launch_vagg_v2(s, false, tl, vB, y1, vL, vR, va, den_v, vb)); ctx->launches += 2; }
+            } else {
+                CUL(launch_vagg_v2(s, it == 0, tl, ylo, yhi, vL, vR, va, den_v, vb, ev_main));
+            }
             ctx->launches += kVHelpers ? 1 : 2;                // main kernel (+ diagonal fix-up kernel) + edge padding kernel
             t.v_end(it);
+            if (overlap && it + 1 < r) {
+                const int h0 = up ? y0 + R : y0, h1 = down ? y1 - R : y1;       // interior rows of the horizontal pass
+                CU(cudaEventRecord(ctx->ev_v, s));
+                CU(cudaStreamWaitEvent(ctx->side, ctx->ev_v, 0));
+                if (up) CUL(launch_hagg_v2(ctx->side, it == 0, tl, y0, h0, hL, hR, vb, den_h, va));
+                if (down) CUL(launch_hagg_v2(ctx->side, it == 0, tl, h1, y1, hL, hR, vb, den_h, va));
+                CU(cudaEventRecord(ctx->ev_hb, ctx->side));
+                if (hx->begin(hx->user, it, up ? va + (size_t)(y0 - ya) * vrow : nullptr, down ? va + (size_t)(y1 - R - ya) * vrow : nullptr,
+                              up ? va + (size_t)(y0 - R - ya) * vrow : nullptr, down ? va + (size_t)(y1 - ya) * vrow : nullptr, hbytes,
+                              (void*)ctx->side))
+                    return fail(ctx, ASW_ERR_CUDA, "halo exchange (begin) callback failed");
+                CUL(launch_hagg_v2(s, it == 0, tl, h0, h1, hL, hR, vb, den_h, va));
+                CU(cudaStreamWaitEvent(s, ctx->ev_hb, 0));     // the next vertical pass reads the boundary rows as well
+                t.h_end(it);
+                continue;
+            }
             CUL(launch_hagg_v2(s, it == 0, tl, ylo, yhi, hL, hR, vb, den_h, va));
             t.h_end(it);
-            if (hx && it + 1 < r) {
+            if (hx && hx->fn && it + 1 < r) {
                 // the next vertical pass reads R rows of each neighbour: hand out our boundary rows (volume rows are contiguous:
                 // Wv * Dp floats each) and where the neighbours' rows go; the callback moves them (NCCL, peer copies ...)
-                const size_t row = (size_t)tl.Wv * tl.Dp, bytes = sizeof(float) * row * R;
-                float* top_send = va + (size_t)(y0 - ya) * row;
-                float* bot_send = va + (size_t)(y1 - R - ya) * row;
-                float* top_recv = y0 > 0 ? va + (size_t)(y0 - R - ya) * row : nullptr;
-                float* bot_recv = y1 < H ? va + (size_t)(y1 - ya) * row : nullptr;
-                const int hs = hx->fn(hx->user, it, y0 > 0 ? top_send : nullptr, y1 < H ? bot_send : nullptr, top_recv, bot_recv, bytes);
+                const int hs = hx->fn(hx->user, it, up ? va + (size_t)(y0 - ya) * vrow : nullptr, down ? va + (size_t)(y1 - R - ya) * vrow : nullptr,
+                                      up ? va + (size_t)(y0 - R - ya) * vrow : nullptr, down ? va + (size_t)(y1 - ya) * vrow : nullptr, hbytes);
                 if (hs) return fail(ctx, ASW_ERR_CUDA, "halo exchange callback failed");
                 t.prev = t.et.mark();                          // the exchange counts towards agg_total_ms, not towards the next V pass
+            } else if (hx && hx->begin && !overlap && it + 1 < r) {
+                // band too short to split: the asynchronous callbacks are used back to back (no overlap)
+                if (hx->begin(hx->user, it, up ? va + (size_t)(y0 - ya) * vrow : nullptr, down ? va + (size_t)(y1 - R - ya) * vrow : nullptr,
+                              up ? va + (size_t)(y0 - R - ya) * vrow : nullptr, down ? va + (size_t)(y1 - ya) * vrow : nullptr, hbytes, (void*)s) ||
+                    hx->end(hx->user, it, (void*)s))
+                    return fail(ctx, ASW_ERR_CUDA, "halo exchange callback failed");
             }
         }
         t.e_agg = t.et.mark();
@@ -397,7 +435,10 @@ int asw_create(asw_ctx** out, int device) {
     if (!ctx) return ASW_ERR_NOMEM;
     ctx->device = device;
     if (cudaGetDeviceProperties(&ctx->prop, device) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_v, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_hb, cudaEventDisableTiming) != cudaSuccess) {
         delete ctx;
         return ASW_ERR_CUDA;
     }
@@ -417,6 +458,10 @@ int asw_destroy(asw_ctx* ctx) {
     for (Scratch& s : ctx->tail) if (s.p) cudaFree(s.p);
     for (Scratch& s : ctx->cb) if (s.p) cudaFree(s.p);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    cudaStreamSynchronize(ctx->side);
+    if (ctx->ev_v) cudaEventDestroy(ctx->ev_v);
+    if (ctx->ev_hb) cudaEventDestroy(ctx->ev_hb);
+    cudaStreamDestroy(ctx->side);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return ASW_OK;
@@ -484,6 +529,28 @@ int asw_disparity_band_exchange_device(asw_ctx* ctx, const uint8_t* dl, const ui
     ctx->keep_volume = keep;
     return st;
 }
+
+int asw_disparity_band_exchange_async_device(asw_ctx* ctx, const uint8_t* dl, const uint8_t* dr, int W, int H, int y0, int y1,
+                                             const asw_params* prm, uint8_t* d_rgba, uint8_t* d_d, float* d_conf,
+                                             asw_halo_begin_fn begin, asw_halo_end_fn end, void* user, asw_timing* tm) {
+    int st = check_params(ctx, W, H, prm);
+    if (st) return st;
+    if (!dl || !dr) return fail(ctx, ASW_ERR_INVALID, "image pointer is NULL");
+    if (!begin || !end) return fail(ctx, ASW_ERR_INVALID, "exchange callback is NULL");
+    if (y0 < 0 || y1 > H || y0 >= y1) return fail(ctx, ASW_ERR_INVALID, "band must satisfy 0 <= y0 < y1 <= H");
+    if ((y0 > 0 || y1 < H) && y1 - y0 < prm->radius) return fail(ctx, ASW_ERR_INVALID, "a band with neighbours needs at least `radius` rows");
+    if (prm->ndisp > 256 && d_d) return fail(ctx, ASW_ERR_UNSUPPORTED, "disp_d is uint8: ndisp <= 256 required");
+    CU(cudaSetDevice(ctx->device));
+    HaloX hx;
+    hx.begin = begin; hx.end = end; hx.user = user;
+    const int keep = ctx->keep_volume;
+    ctx->keep_volume = 0;
+    st = run_band(ctx, dl, dr, W, H, y0, y1, prm, d_rgba, d_d, d_conf, tm, nullptr, &hx);
+    ctx->keep_volume = keep;
+    return st;
+}
+
+void* asw_side_stream(asw_ctx* ctx) { return ctx ? (void*)ctx->side : nullptr; }
 
 int asw_disparity_shard_device(asw_ctx* ctx, const uint8_t* dl, const uint8_t* dr, int W, int H, int y0, int y1, int d0, int d1,
                                const asw_params* prm, float* d_min1, float* d_min2, int* d_arg, asw_timing* tm) {

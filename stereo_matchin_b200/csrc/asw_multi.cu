@@ -7,6 +7,9 @@
 // Nothing is recomputed (the r * R halo of asw_disparity_band_device is replaced by R exchanged rows), so the
 // result is bit-identical to the one-GPU frame.  No collective library is involved: the only exchange of the path is
 // these neighbour copies, and every band writes its rows of the result directly into the caller's host buffers.
+// The copies run on a communication stream per band, ordered by CUDA events across the devices, under the interior
+// rows of the iteration (asw_disparity_band_exchange_async_device); the band threads only meet at host barriers that
+// make sure an event has been RECORDED before a neighbour enqueues a wait on it -- no thread waits for GPU work.
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
@@ -49,6 +52,8 @@ struct BandState {
     void* buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // left, right, out_rgba, out_d, out_conf (device, grown on demand)
     size_t cap[5] = {0, 0, 0, 0, 0};
     void *top_send = nullptr, *bottom_send = nullptr;      // published at every exchange
+    cudaStream_t comm = nullptr;                           // the band's communication stream
+    cudaEvent_t ready = nullptr, done = nullptr;           // boundary rows of this iteration final / this band's pulls complete
     asw_timing tm;
     int status = ASW_OK;
 };
@@ -69,24 +74,43 @@ struct CbArg {
     int i;
 };
 
-// the asw_halo_fn of band i: see asw_disparity_band_exchange_device for the contract
-int exchange_cb(void* user, int, void* top_send, void* bottom_send, void* top_recv, void* bottom_recv, size_t bytes) {
+// asw_halo_begin_fn of band i (contract: asw_disparity_band_exchange_async_device).  `boundary_stream` has the band's
+// border rows of this iteration enqueued.
+int begin_cb(void* user, int, void* top_send, void* bottom_send, void* top_recv, void* bottom_recv, size_t bytes, void* boundary_stream) {
     CbArg* a = (CbArg*)user;
     asw_multi* m = a->m;
-    BandState& b = m->band[a->i];
-    cudaStream_t s = (cudaStream_t)asw_stream(b.ctx);
-    if (cudaStreamSynchronize(s) != cudaSuccess) { m->bar.fail(); return 1; }          // our rows of this iteration are final
+    const int i = a->i;
+    BandState& b = m->band[i];
     b.top_send = top_send;
     b.bottom_send = bottom_send;
-    if (!m->bar.wait()) return 1;                                                      // ... and so are everybody's
-    cudaError_t e = cudaSuccess;
-    if (top_recv && a->i > 0)
-        e = cudaMemcpyPeerAsync(top_recv, b.device, m->band[a->i - 1].bottom_send, m->band[a->i - 1].device, bytes, s);
-    if (e == cudaSuccess && bottom_recv && a->i + 1 < m->n)
-        e = cudaMemcpyPeerAsync(bottom_recv, b.device, m->band[a->i + 1].top_send, m->band[a->i + 1].device, bytes, s);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (cudaEventRecord(b.ready, (cudaStream_t)boundary_stream) != cudaSuccess) { m->bar.fail(); return 1; }
+    if (!m->bar.wait()) return 1;                          // every band has recorded `ready` and published its rows
+    cudaError_t e = cudaStreamWaitEvent(b.comm, b.ready, 0);               // our halo rows are no longer read by our vertical pass
+    if (e == cudaSuccess && top_recv && i > 0) {
+        e = cudaStreamWaitEvent(b.comm, m->band[i - 1].ready, 0);
+        if (e == cudaSuccess) e = cudaMemcpyPeerAsync(top_recv, b.device, m->band[i - 1].bottom_send, m->band[i - 1].device, bytes, b.comm);
+    }
+    if (e == cudaSuccess && bottom_recv && i + 1 < m->n) {
+        e = cudaStreamWaitEvent(b.comm, m->band[i + 1].ready, 0);
+        if (e == cudaSuccess) e = cudaMemcpyPeerAsync(bottom_recv, b.device, m->band[i + 1].top_send, m->band[i + 1].device, bytes, b.comm);
+    }
+    if (e == cudaSuccess) e = cudaEventRecord(b.done, b.comm);
     if (e != cudaSuccess) { m->bar.fail(); return 1; }
-    return m->bar.wait() ? 0 : 1;                                                      // all pulls done: send rows may be rewritten
+    return m->bar.wait() ? 0 : 1;                          // every band has recorded `done`
+}
+
+// asw_halo_end_fn: the main stream waits for our pulls (halo rows complete) and for the neighbours' pulls (our send rows are
+// free: the next horizontal pass rewrites them)
+int end_cb(void* user, int, void* main_stream) {
+    CbArg* a = (CbArg*)user;
+    asw_multi* m = a->m;
+    const int i = a->i;
+    cudaStream_t s = (cudaStream_t)main_stream;
+    cudaError_t e = cudaStreamWaitEvent(s, m->band[i].done, 0);
+    if (e == cudaSuccess && i > 0) e = cudaStreamWaitEvent(s, m->band[i - 1].done, 0);
+    if (e == cudaSuccess && i + 1 < m->n) e = cudaStreamWaitEvent(s, m->band[i + 1].done, 0);
+    if (e != cudaSuccess) { m->bar.fail(); return 1; }
+    return 0;
 }
 
 int ensure_dev(BandState& b, int k, size_t bytes) {
@@ -115,6 +139,13 @@ int asw_multi_create(asw_multi** out, const int* devices, int n) {
         m->band[i].device = devices[i];
         int st = asw_create(&m->band[i].ctx, devices[i]);
         if (st != ASW_OK) { asw_multi_destroy(m); return st; }
+        BandState& b = m->band[i];
+        if (cudaSetDevice(devices[i]) != cudaSuccess || cudaStreamCreateWithFlags(&b.comm, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&b.ready, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming) != cudaSuccess) {
+            asw_multi_destroy(m);
+            return ASW_ERR_CUDA;
+        }
     }
     // neighbours read each other's volumes: peer access makes the copies direct NVLink transfers (without it the
     // runtime stages them through the host, which is still correct)
@@ -139,6 +170,10 @@ int asw_multi_destroy(asw_multi* m) {
         if (!b.ctx) continue;
         for (void* p : b.buf)
             if (p) asw_dev_free(b.ctx, p);
+        cudaSetDevice(b.device);
+        if (b.comm) { cudaStreamSynchronize(b.comm); cudaStreamDestroy(b.comm); }
+        if (b.ready) cudaEventDestroy(b.ready);
+        if (b.done) cudaEventDestroy(b.done);
         asw_destroy(b.ctx);
     }
     delete m;
@@ -190,9 +225,9 @@ int asw_multi_disparity(asw_multi* m, const uint8_t* left, const uint8_t* right,
                                                disp_rgba ? (uint8_t*)out_rgba : nullptr, disp_d ? (uint8_t*)out_d : nullptr,
                                                conf ? (float*)out_conf : nullptr, &b.tm);
             else
-                st = asw_disparity_band_exchange_device(b.ctx, (const uint8_t*)img_l, (const uint8_t*)img_r, W, H, y0, y1, prm,
-                                                        disp_rgba ? (uint8_t*)out_rgba : nullptr, disp_d ? (uint8_t*)out_d : nullptr,
-                                                        conf ? (float*)out_conf : nullptr, exchange_cb, &args[i], &b.tm);
+                st = asw_disparity_band_exchange_async_device(b.ctx, (const uint8_t*)img_l, (const uint8_t*)img_r, W, H, y0, y1, prm,
+                                                              disp_rgba ? (uint8_t*)out_rgba : nullptr, disp_d ? (uint8_t*)out_d : nullptr,
+                                                              conf ? (float*)out_conf : nullptr, begin_cb, end_cb, &args[i], &b.tm);
             if (st) return bail(st);
             if (!m->bar.wait()) return;                        // slowest band: the frame is done on the devices
             if (i == 0) t_done = clk::now();

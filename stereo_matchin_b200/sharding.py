@@ -291,12 +291,55 @@ def cuda_exchange_fn(ctx, rank: int, world: int, group=None, device=None):
     return fn
 
 
+class CudaHaloOverlap:
+    """The product's callbacks for AswContext.disparity_band_exchange_async: the halo rows travel (NCCL send/recv on a
+    communication stream of this rank) while the library aggregates the interior rows; nothing blocks the host.
+      begin: the communication stream waits for the library's boundary stream (the band's border rows of this iteration),
+             then the batched isend/irecv is enqueued on it;
+      end:   the library's main stream waits for the communication stream (rows received, send rows free)."""
+
+    def __init__(self, rank: int, world: int, group=None, device=None):
+        import torch
+        self.rank, self.world, self.group = rank, world, group
+        self.dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.comm = torch.cuda.Stream(device=self.dev)
+        self.keep = []                                   # tensor views of the library's rows, alive until the transfer is over
+
+    def begin(self, _it, top_send, bottom_send, top_recv, bottom_recv, nbytes, boundary_stream):
+        import torch
+        import torch.distributed as dist
+        view = lambda p: None if not p else torch.as_tensor(_DevView(p, nbytes), device=self.dev)
+        ts, bs, tr, br = view(top_send), view(bottom_send), view(top_recv), view(bottom_recv)
+        self.keep = [ts, bs, tr, br]
+        self.comm.wait_stream(torch.cuda.ExternalStream(boundary_stream, device=self.dev))
+        ops = []
+        if self.rank > 0:
+            ops += [dist.P2POp(dist.isend, ts, self.rank - 1, self.group), dist.P2POp(dist.irecv, tr, self.rank - 1, self.group)]
+        if self.rank + 1 < self.world:
+            ops += [dist.P2POp(dist.isend, bs, self.rank + 1, self.group), dist.P2POp(dist.irecv, br, self.rank + 1, self.group)]
+        with torch.cuda.stream(self.comm):
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()                               # NCCL: orders the communication stream after the transfer, does not block the host
+
+    def end(self, _it, main_stream):
+        import torch
+        torch.cuda.ExternalStream(main_stream, device=self.dev).wait_stream(self.comm)
+
+
 def disparity_row_exchange_cuda(ctx, d_left: int, d_right: int, W: int, H: int, params, rank: int, world: int, out_band,
-                                group=None, timing: bool = False):
+                                group=None, timing: bool = False, overlap: bool = False):
     """This rank's band of one frame with halo exchange (device pointers of the FULL images in, `out_band` = torch uint8
     tensor (rows, W) on this rank's GPU out).  Returns the library's timing dict if asked.  Bands: row_bands(H, world)."""
+    # `overlap`: hide the exchange under the interior rows (CudaHaloOverlap).  Measured on 8 B200s with NCCL 2.27 it LOSES
+    # to the host-synchronous exchange (25.6 vs 23.7 ms on the 4K frame): NCCL's send/recv kernels occupy SMs, and the
+    # persistent vertical-pass grid (one CTA per SM, static tile list) then runs with late CTAs.  The in-process path
+    # (asw_multi_*: copy-engine peer copies ordered by events) does profit from the overlap (20.7 ms).
     y0, y1 = row_bands(H, world)[rank]
     if world == 1:
         return ctx.disparity_raw(d_left, d_right, W, H, params, None, out_band.data_ptr(), None, timing=timing)
+    if overlap:
+        ops = CudaHaloOverlap(rank, world, group)
+        return ctx.disparity_band_exchange_async(d_left, d_right, W, H, params, (y0, y1), None, out_band.data_ptr(), None, ops.begin, ops.end,
+                                                 timing=timing)
     return ctx.disparity_band_exchange(d_left, d_right, W, H, params, (y0, y1), None, out_band.data_ptr(), None,
                                        cuda_exchange_fn(ctx, rank, world, group), timing=timing)

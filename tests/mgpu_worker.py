@@ -23,15 +23,18 @@ def main():
     dl, dr = torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda()
     y0, y1 = sharding.row_bands(H, world)[rank]
     band = torch.empty((y1 - y0, W), dtype=torch.uint8, device="cuda")
-    sharding.disparity_row_exchange_cuda(ctx, dl.data_ptr(), dr.data_ptr(), W, H, p, rank, world, band)
-    ctx.sync()
-    full = sharding.gather_bands(band, H, W, rank, world)
+    fulls = []
+    for overlap in (True, False):       # exchange hidden under the interior rows / host-synchronous exchange
+        band.zero_()
+        sharding.disparity_row_exchange_cuda(ctx, dl.data_ptr(), dr.data_ptr(), W, H, p, rank, world, band, overlap=overlap)
+        ctx.sync()
+        fulls.append(sharding.gather_bands(band, H, W, rank, world))
     ok = True
     if rank == 0:
         one = torch.empty((H, W), dtype=torch.uint8, device="cuda")
         ctx.disparity_raw(dl.data_ptr(), dr.data_ptr(), W, H, p, None, one.data_ptr(), None)
         ctx.sync()
-        ok = bool(torch.equal(full, one))
+        ok = all(bool(torch.equal(f, one)) for f in fulls)
         print("equals_1gpu", ok, "world", world, flush=True)
     dist.barrier()
     dist.destroy_process_group()

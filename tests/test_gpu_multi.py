@@ -138,3 +138,23 @@ def test_cfg5_frame_vs_oracle(ctx, oracle):
     assert_bit_equal(g["d"].astype(np.float32), o["d_ref"], "cfg5 frame vs oracle: disparity")
     assert_bit_equal(g["conf"], o["conf_ref"], "cfg5 frame vs oracle: confidence")
     assert_bit_equal(g["left"], o["left"], "cfg5 frame vs oracle: disparity image")
+
+
+def test_host_binary_devices_option(tmp_path):
+    """src/host/stereo_matching --devices 0,0 --method hot: every frame is split over the listed devices (here: two bands
+    on device 0) and the PNG equals the one written with --device 0."""
+    import shutil
+    from conftest import GOLDEN, PAIRS, load_rgba
+    exe = os.path.join(ROOT, "src", "host", "stereo_matching")
+    assert os.path.exists(exe), "run `python -m stereo_matchin_b200.build` first"
+    os.makedirs(tmp_path / "teddy")
+    for f in PAIRS["teddy"]:
+        shutil.copy(os.path.join(GOLDEN, "teddy", f), tmp_path / "teddy" / f)
+    (tmp_path / "pics.txt").write_text("teddy/im2.png\nteddy/im6.png\n")
+    outs = {}
+    for tag, dev in (("one", ["--device", "0"]), ("two", ["--devices", "0,0"])):
+        r = subprocess.run([exe, "--pics", str(tmp_path / "pics.txt"), "--root", str(tmp_path), "--runs", "2", "--method", "hot",
+                            "--out-suffix", "_" + tag, "--log", str(tmp_path / (tag + ".tsv"))] + dev, capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs[tag] = load_rgba(str(tmp_path / "teddy" / ("asw_disparity_" + tag + ".png")))
+    assert np.array_equal(outs["one"], outs["two"])
