@@ -116,7 +116,7 @@ def make_config_dict(args, W, H, D, pairs_per_rank, sharding_desc, Dp):
     return {"workload": f"{args.workload}: {desc}", "W": W, "H": H, "ndisp": D, "radius": 16, "iterations": args.iterations,
             "pairs_per_rank": pairs_per_rank, "sharding": sharding_desc,
             "l2": "inputs larger than L2: every pass streams a %.2f GB cost volume" % (4.0 * W * H * Dp / 1e9),
-            "kernel_family": {0: "tma", 1: "basic", 2: "tiled"}[args.family],
+            "kernel_family": {0: "tma", 1: "basic"}[args.family],
             "reference_sample": "the reference arm (--impl reference) and cpu_baseline time the CPU port on the top %d of %d rows "
                                 "of the same pair, all host threads" % (min(H, max(33, int(args.ref_rows))), H)}
 
@@ -328,7 +328,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--iterations", type=int, default=7)
-    ap.add_argument("--family", type=int, default=0, help="0 = TMA-fed kernels (default), 1 = basic kernels, 2 = tiled kernels without TMA")
+    ap.add_argument("--family", type=int, default=0, choices=[0, 1], help="0 = TMA-fed kernels (default), 1 = generic kernels")
     ap.add_argument("--cpu-rows", type=int, default=400, help="rows of the pair the CPU baseline sample covers")
     ap.add_argument("--ref-rows", type=int, default=400)
     ap.add_argument("--no-cpu-baseline", action="store_true")

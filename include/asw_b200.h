@@ -343,9 +343,9 @@ ASW_API int asw_host_alloc(asw_ctx* ctx, void** h_ptr, size_t bytes);
 ASW_API int asw_host_free(asw_ctx* ctx, void* h_ptr);
 
 /* Selects the kernel family of the fused path: 0 = automatic (default: the TMA-fed sm_100a kernels for
- * radius 16, ndisp padded to a multiple of 64 internally), 1 = the straightforward one-thread-per-output
- * kernels of the per-operator entry points, 2 = the earlier tiled kernels without TMA (1 and 2 are kept as
- * on-device cross-checks).  All are CUDA; none is a CPU path. */
+ * radius 16, ndisp padded to a multiple of 64 internally; the generic kernels for any other radius),
+ * 1 = the generic one-thread-per-output kernels for every radius (an on-device cross-check of family 0).
+ * Both are CUDA; there is no CPU path. */
 ASW_API int asw_set_kernel_family(asw_ctx* ctx, int family);
 
 #ifdef __cplusplus

@@ -92,6 +92,7 @@ unsigned decode(std::vector<unsigned char>& out, unsigned& w, unsigned& h, const
         pos += 12 + (size_t)len;
     }
     if (!have_ihdr || w == 0 || h == 0) return kHeader;
+    if (w > 65535u || h > 65535u) return kUnsupported;          // the library limits H to 65535; also bounds the allocation below
     if (bit_depth != 8 || interlace != 0) return kUnsupported;
     unsigned ch;
     switch (color_type) {

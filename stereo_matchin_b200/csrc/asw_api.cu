@@ -13,7 +13,6 @@
 #include "../../include/asw_b200.h"
 #include "asw_common.cuh"
 #include "asw_kernels_basic.cuh"
-#include "asw_kernels_tiled.cuh"
 #include "asw_kernels_tma.cuh"
 #include "asw_kernels_tail.cuh"
 #include "asw_kernels_cross.cuh"
@@ -32,6 +31,7 @@ struct Scratch {
 struct asw_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    LaunchEnv env;                         // SM count + cached tensor maps of this context
     cudaStream_t side = nullptr;            // second stream: boundary rows of the horizontal pass under the interior rows (halo overlap)
     cudaEvent_t ev_v = nullptr, ev_hb = nullptr;
     cudaDeviceProp prop{};
@@ -91,6 +91,8 @@ int check_params(asw_ctx* ctx, int W, int H, const asw_params* p) {
     if (W <= 0 || H <= 0) return fail(ctx, ASW_ERR_INVALID, "W and H must be positive");
     if (p->ndisp <= 0 || p->radius < 0 || p->iterations < 0) return fail(ctx, ASW_ERR_INVALID, "ndisp > 0, radius >= 0, iterations >= 0 required");
     if (!(p->gamma_c > 0.0f) || !(p->gamma_p > 0.0f)) return fail(ctx, ASW_ERR_INVALID, "gamma_c and gamma_p must be positive");
+    // raw costs must be positive and normal for the branch-free division of the fused kernels (div_rn_normal); NaN fails the test too
+    if (!(p->trunc > 0.0f)) return fail(ctx, ASW_ERR_INVALID, "trunc must be positive (INFINITY = no truncation)");
     if (p->ndisp > 65535 || H > 65535) return fail(ctx, ASW_ERR_UNSUPPORTED, "ndisp and H are limited to 65535");
     if (p->radius > 64) return fail(ctx, ASW_ERR_UNSUPPORTED, "radius is limited to 64");
     return ASW_OK;
@@ -220,9 +222,8 @@ int run_band(asw_ctx* ctx, const uint8_t* dl, const uint8_t* dr, int W, int H, i
     const bool tma = ctx->family == 0 && tma_supported(R, Dfull);
     if (sh && !tma) return fail(ctx, ASW_ERR_UNSUPPORTED, "disparity shards need the TMA kernel family (radius 16, family 0)");
     if (hx && !tma) return fail(ctx, ASW_ERR_UNSUPPORTED, "the halo exchange needs the TMA kernel family (radius 16, family 0)");
-    const bool tiled = !tma && (ctx->family == 0 || ctx->family == 2) && tiled_supported(R);
     const TL tl = make_tl(b, Dfull, sd0, sd1);
-    const int Dp = tma ? tma_padded_D(D) : tiled ? padded_D(D) : D;
+    const int Dp = tma ? tma_padded_D(D) : D;
     const size_t vol_bytes = sizeof(float) * (tma ? tl.vol_elems() : b.plane() * (size_t)Dp);
     const size_t tab_bytes = sizeof(float) * b.plane() * (size_t)T;
     int st;
@@ -234,11 +235,11 @@ int run_band(asw_ctx* ctx, const uint8_t* dl, const uint8_t* dr, int W, int H, i
     } else if ((st = ensure(ctx, ctx->vL, tab_bytes)) || (st = ensure(ctx, ctx->hL, tab_bytes)) ||
                (st = ensure(ctx, ctx->vR, tab_bytes)) || (st = ensure(ctx, ctx->hR, tab_bytes)))
         return st;
-    for (int i = 0; i < ((tiled || tma) ? 2 : 3); i++)
+    for (int i = 0; i < (tma ? 2 : 3); i++)
         if ((st = ensure(ctx, ctx->vol[i], vol_bytes))) return st;
     // the TMA family keeps the vertical denominators in a private per-thread layout (vden_* in asw_kernels_tma.cuh)
     const size_t denv_bytes = tma ? sizeof(float) * vden_total_floats(W, b.y_off, b.Hb, Dp) : vol_bytes;
-    if ((tiled || tma) && r > 0 && ((st = ensure(ctx, ctx->den_v, denv_bytes)) || (st = ensure(ctx, ctx->den_h, vol_bytes)))) return st;
+    if (tma && r > 0 && ((st = ensure(ctx, ctx->den_v, denv_bytes)) || (st = ensure(ctx, ctx->den_h, vol_bytes)))) return st;
     float *vL = (float*)ctx->vL.p, *hL = (float*)ctx->hL.p, *vR = (float*)ctx->vR.p, *hR = (float*)ctx->hR.p;
 
     ctx->launches = 0;
@@ -280,12 +281,12 @@ int run_band(asw_ctx* ctx, const uint8_t* dl, const uint8_t* dr, int W, int H, i
                 ev_main = ctx->ev[t.ev_vmain[it]];
             }
             if (overlap && it > 0) {
-                CUL(launch_vagg_v2(s, false, tl, vA, vB, vL, vR, va, den_v, vb, ev_main));
+                CUL(launch_vagg_v2(s, false, tl, vA, vB, vL, vR, va, den_v, vb, ev_main, &ctx->env));
                 if (hx->end(hx->user, it - 1, (void*)s)) return fail(ctx, ASW_ERR_CUDA, "halo exchange (end) callback failed");
-                if (vA > y0) { CUL(launch_vagg_v2(s, false, tl, y0, vA, vL, vR, va, den_v, vb)); ctx->launches += 2; }
-                if (y1 > vB) { CUL(launch_vagg_v2(s, false, tl, vB, y1, vL, vR, va, den_v, vb)); ctx->launches += 2; }
+                if (vA > y0) { CUL(launch_vagg_v2(s, false, tl, y0, vA, vL, vR, va, den_v, vb, nullptr, &ctx->env)); ctx->launches += 2; }
+                if (y1 > vB) { CUL(launch_vagg_v2(s, false, tl, vB, y1, vL, vR, va, den_v, vb, nullptr, &ctx->env)); ctx->launches += 2; }
             } else {
-                CUL(launch_vagg_v2(s, it == 0, tl, ylo, yhi, vL, vR, va, den_v, vb, ev_main));
+                CUL(launch_vagg_v2(s, it == 0, tl, ylo, yhi, vL, vR, va, den_v, vb, ev_main, &ctx->env));
             }
             ctx->launches += kVHelpers ? 1 : 2;                // main kernel (+ diagonal fix-up kernel) + edge padding kernel
             t.v_end(it);
@@ -293,19 +294,19 @@ int run_band(asw_ctx* ctx, const uint8_t* dl, const uint8_t* dr, int W, int H, i
                 const int h0 = up ? y0 + R : y0, h1 = down ? y1 - R : y1;       // interior rows of the horizontal pass
                 CU(cudaEventRecord(ctx->ev_v, s));
                 CU(cudaStreamWaitEvent(ctx->side, ctx->ev_v, 0));
-                if (up) CUL(launch_hagg_v2(ctx->side, it == 0, tl, y0, h0, hL, hR, vb, den_h, va));
-                if (down) CUL(launch_hagg_v2(ctx->side, it == 0, tl, h1, y1, hL, hR, vb, den_h, va));
+                if (up) CUL(launch_hagg_v2(ctx->side, it == 0, tl, y0, h0, hL, hR, vb, den_h, va, &ctx->env));
+                if (down) CUL(launch_hagg_v2(ctx->side, it == 0, tl, h1, y1, hL, hR, vb, den_h, va, &ctx->env));
                 CU(cudaEventRecord(ctx->ev_hb, ctx->side));
                 if (hx->begin(hx->user, it, up ? va + (size_t)(y0 - ya) * vrow : nullptr, down ? va + (size_t)(y1 - R - ya) * vrow : nullptr,
                               up ? va + (size_t)(y0 - R - ya) * vrow : nullptr, down ? va + (size_t)(y1 - ya) * vrow : nullptr, hbytes,
                               (void*)ctx->side))
                     return fail(ctx, ASW_ERR_CUDA, "halo exchange (begin) callback failed");
-                CUL(launch_hagg_v2(s, it == 0, tl, h0, h1, hL, hR, vb, den_h, va));
+                CUL(launch_hagg_v2(s, it == 0, tl, h0, h1, hL, hR, vb, den_h, va, &ctx->env));
                 CU(cudaStreamWaitEvent(s, ctx->ev_hb, 0));     // the next vertical pass reads the boundary rows as well
                 t.h_end(it);
                 continue;
             }
-            CUL(launch_hagg_v2(s, it == 0, tl, ylo, yhi, hL, hR, vb, den_h, va));
+            CUL(launch_hagg_v2(s, it == 0, tl, ylo, yhi, hL, hR, vb, den_h, va, &ctx->env));
             t.h_end(it);
             if (hx && hx->fn && it + 1 < r) {
                 // the next vertical pass reads R rows of each neighbour: hand out our boundary rows (volume rows are contiguous:
@@ -328,35 +329,6 @@ int run_band(asw_ctx* ctx, const uint8_t* dl, const uint8_t* dr, int W, int H, i
         if (ctx->keep_volume) {
             if ((st = ensure(ctx, ctx->vol_ref, sizeof(float) * (size_t)W * (y1 - y0) * D))) return st;
             CUL(launch_volume_to_ref_v2(s, tl, y0, y1, va, (float*)ctx->vol_ref.p));
-            fin = (const float*)ctx->vol_ref.p;
-        }
-    } else if (tiled) {
-        float *va = (float*)ctx->vol[0].p, *vb = (float*)ctx->vol[1].p;
-        float *den_v = (float*)ctx->den_v.p, *den_h = (float*)ctx->den_h.p;
-        cudaStream_t s = ctx->stream;
-        CUL(launch_raw_t(s, dl, dr, b, ya, yb, D, p->trunc, va));
-        t.e_raw = t.et.mark();
-        CUL(launch_support_t(s, true, dl, b, ya, yb, p->gamma_c, p->gamma_p, vL));
-        CUL(launch_support_t(s, false, dl, b, ya, yb, p->gamma_c, p->gamma_p, hL));
-        CUL(launch_support_t(s, true, dr, b, ya, yb, p->gamma_c, p->gamma_p, vR));
-        CUL(launch_support_t(s, false, dr, b, ya, yb, p->gamma_c, p->gamma_p, hR));
-        t.prev = t.e_supp = t.et.mark();
-        // V reads va, writes vb; H reads vb, writes va (its input was consumed by V already).
-        for (int it = 0; it < r; it++) {
-            const int ylo = max(ya, y0 - (r - 1 - it) * R), yhi = min(yb, y1 + (r - 1 - it) * R);
-            t.v_begin(it);
-            CUL(launch_vagg_t(s, it == 0, b, ylo, yhi, D, vL, vR, va, den_v, vb));
-            t.v_end(it);
-            CUL(launch_hagg_t(s, it == 0, b, ylo, yhi, D, hL, hR, vb, den_h, va));
-            t.h_end(it);
-        }
-        t.e_agg = t.et.mark();
-        CUL(launch_wta_t(s, b, y0, y1, y0, D, va, d_rgba, d_d, d_conf));
-        t.e_wta = t.et.mark();
-        if (ctx->keep_volume) {
-            // hand the final volume out in the reference layout (x + W*y + W*rows*d, rows = y1-y0)
-            if ((st = ensure(ctx, ctx->vol_ref, sizeof(float) * (size_t)W * (y1 - y0) * D))) return st;
-            CUL(launch_volume_to_ref(s, b, y0, y1, D, va, (float*)ctx->vol_ref.p));
             fin = (const float*)ctx->vol_ref.p;
         }
     } else {
@@ -386,9 +358,9 @@ int run_band(asw_ctx* ctx, const uint8_t* dl, const uint8_t* dr, int W, int H, i
             if (ya == y0 && yb == y1) fin = in;
             else {
                 if ((st = ensure(ctx, ctx->vol_ref, sizeof(float) * (size_t)W * (y1 - y0) * D))) return st;
-                for (int d = 0; d < D; d++)
-                    CU(cudaMemcpyAsync((float*)ctx->vol_ref.p + (size_t)d * W * (y1 - y0), in + (size_t)d * b.plane() + (size_t)(y0 - ya) * W,
-                                       sizeof(float) * (size_t)W * (y1 - y0), cudaMemcpyDeviceToDevice, ctx->stream));
+                // rows [y0,y1) of every disparity plane: one strided copy (source pitch = a band plane, destination pitch = the rows kept)
+                CU(cudaMemcpy2DAsync(ctx->vol_ref.p, sizeof(float) * (size_t)W * (y1 - y0), in + (size_t)(y0 - ya) * W, sizeof(float) * b.plane(),
+                                     sizeof(float) * (size_t)W * (y1 - y0), (size_t)D, cudaMemcpyDeviceToDevice, ctx->stream));
                 fin = (const float*)ctx->vol_ref.p;
             }
         }
@@ -443,7 +415,8 @@ int asw_create(asw_ctx** out, int device) {
         return ASW_ERR_CUDA;
     }
     for (auto& ev : ctx->ev) cudaEventCreate(&ev);
-    if (tiled_configure() != cudaSuccess || tma_configure() != cudaSuccess) { cudaGetLastError(); asw_destroy(ctx); return ASW_ERR_CUDA; }
+    ctx->env.sms = ctx->prop.multiProcessorCount;
+    if (tma_configure() != cudaSuccess) { cudaGetLastError(); asw_destroy(ctx); return ASW_ERR_CUDA; }
     *out = ctx;
     return ASW_OK;
 }
@@ -486,7 +459,7 @@ int asw_device_info(asw_ctx* ctx, int* sm_count, int* sm_clock_khz, size_t* tota
 }
 
 int asw_set_kernel_family(asw_ctx* ctx, int family) {
-    if (!ctx || family < 0 || family > 2) return ASW_ERR_INVALID;
+    if (!ctx || family < 0 || family > 1) return ASW_ERR_INVALID;
     ctx->family = family;
     return ASW_OK;
 }
@@ -847,9 +820,9 @@ int check_cross(asw_ctx* ctx, int W, int H, const asw_cross_params* p) {
 }  // namespace
 
 int asw_Median_grid(asw_ctx* ctx, int W, int H, int local, const uint8_t* in, uint8_t* out) {
+    if (ctx && local < 1) return fail(ctx, ASW_ERR_INVALID, "local must be >= 1");
     int st = asw_Median(ctx, W, H, in, out);
     if (st) return st;
-    if (local < 1) return fail(ctx, ASW_ERR_INVALID, "local must be >= 1");
     const int We = local * (W / local), He = local * (H / local);
     if (We < W || He < H) {
         k_cb_zero_border<<<dim3((W + 127) / 128, H), 128, 0, ctx->stream>>>((uint32_t*)out, W, H, We, He);

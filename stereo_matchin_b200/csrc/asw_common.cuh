@@ -11,6 +11,14 @@
 
 namespace asw {
 
+constexpr int kR = 16;             // the reference's window radius (asw_vsupport.cl:19): the fused kernels are specialised for it
+constexpr int kT = 2 * kR + 1;     // 33 taps
+
+template <typename K>
+inline cudaError_t set_smem(K kernel, size_t bytes) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
 // A row band of a W x H frame held in band-local buffers: global row y lives at local row
 // y - y_off, the buffers have Hb rows.  For a whole frame y_off = 0, Hb = H.
 struct Band {

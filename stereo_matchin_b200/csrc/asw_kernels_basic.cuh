@@ -1,6 +1,6 @@
 // asw_kernels_basic.cuh -- one-thread-per-output CUDA kernels with the reference's data
 // layouts.  They back the per-operator C-ABI entry points (asw_Aggr, asw_vSupport, ...),
-// work for any radius / ndisp / pitch, and serve as the on-device cross-check of the tiled
+// work for any radius / ndisp / pitch, and serve as the on-device cross-check of the TMA-fed
 // kernels (kernel family 1).  Threads map to x fastest so every global access is coalesced.
 #pragma once
 #include "asw_common.cuh"
