@@ -619,38 +619,135 @@ static int disparity_host(asw_ctx* ctx, const uint8_t* left, const uint8_t* righ
     CU(cudaSetDevice(ctx->device));                                       \
     Band b{W, H, 0, H};
 
+}  // extern "C"
+
+namespace {
+// For the reference's window (radius 16) and the default kernel family the operators run on the TMA-fed sm_100a kernels:
+// inputs in the reference layouts are re-laid out into the kernels' own layouts on the way in (k_pack_support,
+// k_ref_to_volume_v2), results on the way out (k_volume_to_ref_v2, k_vden_to_ref).  Any other radius, or
+// asw_set_kernel_family(ctx, 1), uses the generic one-thread-per-output kernels (asw_kernels_basic.cuh).
+bool op_tma(asw_ctx* ctx, const asw_params* prm) { return ctx->family == 0 && tma_supported(prm->radius, prm->ndisp); }
+
+int op_unpack(asw_ctx* ctx, const uint8_t* img, int W, int H, Scratch& dst) {
+    int st = ensure(ctx, dst, sizeof(float) * 4 * (size_t)W * H);
+    if (st) return st;
+    CUL(launch_unpack_v2(ctx->stream, img, W * H, (float4*)dst.p));
+    return ASW_OK;
+}
+
+int op_ref_to_volume(asw_ctx* ctx, const TL& tl, const float* ref, float* vol) {
+    dim3 blk(32, 32), grd((tl.W + 31) / 32, (tl.Dp + 31) / 32, tl.H);
+    k_ref_to_volume_v2<<<grd, blk, 0, ctx->stream>>>(ref, tl, vol);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return ASW_OK;
+}
+
+template <bool VERTICAL, bool RIGHT>
+int op_pack_support(asw_ctx* ctx, const TL& tl, const float* ref, float* out) {
+    const int ncols = VERTICAL ? (RIGHT ? tl.WR4 : tl.WL4) : (RIGHT ? tl.NCB * 32 : tl.NXB * 32);
+    k_pack_support<VERTICAL, RIGHT><<<dim3((ncols + 127) / 128, tl.H), 128, 0, ctx->stream>>>(ref, tl, out);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return ASW_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
 int asw_Aggr(asw_ctx* ctx, const uint8_t* l, const uint8_t* r, int W, int H, const asw_params* prm, float* cost) {
     OP_PROLOGUE(l && r && cost)
-    return launch_raw(ctx, l, r, b, 0, H, prm, cost);
+    if (!op_tma(ctx, prm)) return launch_raw(ctx, l, r, b, 0, H, prm, cost);
+    const TL tl = make_tl(b, prm->ndisp);
+    if ((st = op_unpack(ctx, l, W, H, ctx->fimg_l)) || (st = op_unpack(ctx, r, W, H, ctx->fimg_r)) ||
+        (st = ensure(ctx, ctx->vol[0], sizeof(float) * tl.vol_elems())))
+        return st;
+    CUL(launch_raw_v2(ctx->stream, (const float4*)ctx->fimg_l.p, (const float4*)ctx->fimg_r.p, tl, 0, H, prm->trunc, (float*)ctx->vol[0].p));
+    CUL(launch_volume_to_ref_v2(ctx->stream, tl, 0, H, (const float*)ctx->vol[0].p, cost));
+    return ASW_OK;
+}
+
+static int op_support(asw_ctx* ctx, bool vertical, const uint8_t* img, int W, int H, const asw_params* prm, float* out) {
+    int st = op_unpack(ctx, img, W, H, ctx->fimg_l);
+    if (st) return st;
+    dim3 grd((W + 127) / 128, H);
+    if (vertical) k_support_ref<true><<<grd, 128, 0, ctx->stream>>>((const float4*)ctx->fimg_l.p, W, H, prm->gamma_c, prm->gamma_p, out);
+    else k_support_ref<false><<<grd, 128, 0, ctx->stream>>>((const float4*)ctx->fimg_l.p, W, H, prm->gamma_c, prm->gamma_p, out);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return ASW_OK;
 }
 
 int asw_vSupport(asw_ctx* ctx, const uint8_t* img, int W, int H, const asw_params* prm, float* out) {
     OP_PROLOGUE(img && out)
-    return launch_support(ctx, true, img, b, 0, H, prm, out);
+    if (!op_tma(ctx, prm)) return launch_support(ctx, true, img, b, 0, H, prm, out);
+    return op_support(ctx, true, img, W, H, prm, out);
 }
 
 int asw_hSupport(asw_ctx* ctx, const uint8_t* img, int W, int H, const asw_params* prm, float* out) {
     OP_PROLOGUE(img && out)
-    return launch_support(ctx, false, img, b, 0, H, prm, out);
+    if (!op_tma(ctx, prm)) return launch_support(ctx, false, img, b, 0, H, prm, out);
+    return op_support(ctx, false, img, W, H, prm, out);
 }
 
 int asw_vCostAggregation(asw_ctx* ctx, int W, int H, const asw_params* prm, const float* sl, const float* sr,
                          const float* cin, float* den, float* cout) {
     OP_PROLOGUE(sl && sr && cin && cout)
-    return launch_agg_basic(ctx, true, b, 0, H, prm, sl, sr, cin, den, cout);
+    if (!op_tma(ctx, prm)) return launch_agg_basic(ctx, true, b, 0, H, prm, sl, sr, cin, den, cout);
+    const TL tl = make_tl(b, prm->ndisp);
+    if ((st = ensure(ctx, ctx->vL, sizeof(float) * tl.wvl_elems())) || (st = ensure(ctx, ctx->vR, sizeof(float) * tl.wvr_elems())) ||
+        (st = ensure(ctx, ctx->vol[0], sizeof(float) * tl.vol_elems())) || (st = ensure(ctx, ctx->vol[1], sizeof(float) * tl.vol_elems())) ||
+        (st = ensure(ctx, ctx->den_v, sizeof(float) * vden_total_floats(W, 0, H, tl.Dp))))
+        return st;
+    float *vL = (float*)ctx->vL.p, *vR = (float*)ctx->vR.p, *va = (float*)ctx->vol[0].p, *vb = (float*)ctx->vol[1].p, *dv = (float*)ctx->den_v.p;
+    if ((st = op_pack_support<true, false>(ctx, tl, sl, vL)) || (st = op_pack_support<true, true>(ctx, tl, sr, vR)) ||
+        (st = op_ref_to_volume(ctx, tl, cin, va)))
+        return st;
+    CUL(launch_vagg_v2(ctx->stream, true, tl, 0, H, vL, vR, va, dv, vb, nullptr, &ctx->env));   // asw_vcost_aggregation.cl:11-44
+    ctx->launches += kVHelpers ? 1 : 2;
+    CUL(launch_volume_to_ref_v2(ctx->stream, tl, 0, H, vb, cout));
+    if (den) {                                                                                  // output_denom (:43)
+        k_vden_to_ref<<<dim3((W + 127) / 128, H, prm->ndisp), 128, 0, ctx->stream>>>(dv, tl, den);
+        ctx->launches++;
+        CU(cudaGetLastError());
+    }
+    return ASW_OK;
 }
 
 int asw_hCostAggregation(asw_ctx* ctx, int W, int H, const asw_params* prm, const float* sl, const float* sr,
                          const float* vcost, const float* denom_v, float* cout) {
     (void)denom_v;  // accepted and ignored, as in asw_hcost_aggregation.cl:17
     OP_PROLOGUE(sl && sr && vcost && cout)
-    return launch_agg_basic(ctx, false, b, 0, H, prm, sl, sr, vcost, nullptr, cout);
+    if (!op_tma(ctx, prm)) return launch_agg_basic(ctx, false, b, 0, H, prm, sl, sr, vcost, nullptr, cout);
+    const TL tl = make_tl(b, prm->ndisp);
+    if ((st = ensure(ctx, ctx->hL, sizeof(float) * tl.whl_elems())) || (st = ensure(ctx, ctx->hR, sizeof(float) * tl.whr_elems())) ||
+        (st = ensure(ctx, ctx->vol[0], sizeof(float) * tl.vol_elems())) || (st = ensure(ctx, ctx->vol[1], sizeof(float) * tl.vol_elems())) ||
+        (st = ensure(ctx, ctx->den_h, sizeof(float) * tl.vol_elems())))
+        return st;
+    float *hL = (float*)ctx->hL.p, *hR = (float*)ctx->hR.p, *va = (float*)ctx->vol[0].p, *vb = (float*)ctx->vol[1].p;
+    if ((st = op_pack_support<false, false>(ctx, tl, sl, hL)) || (st = op_pack_support<false, true>(ctx, tl, sr, hR)) ||
+        (st = op_ref_to_volume(ctx, tl, vcost, va)))
+        return st;
+    k_vpad_v2<<<H, 256, 0, ctx->stream>>>(tl, va, 0, H);                                        // CLAMP_TO_EDGE columns of the input
+    ctx->launches++;
+    CUL(launch_hagg_v2(ctx->stream, true, tl, 0, H, hL, hR, va, (float*)ctx->den_h.p, vb, &ctx->env));   // asw_hcost_aggregation.cl:12-44
+    CUL(launch_volume_to_ref_v2(ctx->stream, tl, 0, H, vb, cout));
+    return ASW_OK;
 }
 
 int asw_WTA(asw_ctx* ctx, int W, int H, const asw_params* prm, const float* cost, uint8_t* out_rgba, float* d_ref,
             float* d_tar, uint8_t* out_tar_rgba, float* conf_ref, float* conf_tar) {
     OP_PROLOGUE(cost)
-    return launch_wta(ctx, b, 0, H, 0, prm, cost, out_rgba, nullptr, d_ref, d_tar, out_tar_rgba, conf_ref, conf_tar);
+    if (!op_tma(ctx, prm)) return launch_wta(ctx, b, 0, H, 0, prm, cost, out_rgba, nullptr, d_ref, d_tar, out_tar_rgba, conf_ref, conf_tar);
+    if (out_rgba || d_ref || conf_ref) {                       // left part (asw_wta.cl:25-47): warp-shuffle two-minimum scan
+        const TL tl = make_tl(b, prm->ndisp);
+        if ((st = ensure(ctx, ctx->vol[0], sizeof(float) * tl.vol_elems())) || (st = op_ref_to_volume(ctx, tl, cost, (float*)ctx->vol[0].p))) return st;
+        CUL(launch_wta_v2(ctx->stream, tl, 0, H, 0, prm->ndisp, (const float*)ctx->vol[0].p, out_rgba, nullptr, conf_ref, nullptr, nullptr, nullptr, d_ref));
+    }
+    if (d_tar || out_tar_rgba || conf_tar)                     // right / target part (:50-67) walks a data-dependent diagonal of the reference layout
+        return launch_wta(ctx, b, 0, H, 0, prm, cost, nullptr, nullptr, nullptr, d_tar, out_tar_rgba, nullptr, conf_tar);
+    return ASW_OK;
 }
 
 // ---- consumers of the hot path -----------------------------------------------------------------

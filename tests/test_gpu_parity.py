@@ -77,8 +77,16 @@ OP_CASES = [("teddy", 0, 0, 96, 40, 61), ("cones", 300, 200, 150, 37, 61), ("tsu
             ("teddy", 7, 9, 35, 1, 3), ("cones", 0, 0, 70, 70, 1)]
 
 
+@pytest.fixture(params=[0, 1], ids=["tma", "basic"])
+def op_family(ctx, request):
+    """The per-operator entry points on the TMA-fed kernels (layouts converted at the boundary) and on the generic kernels."""
+    ctx.set_kernel_family(request.param)
+    yield request.param
+    ctx.set_kernel_family(0)
+
+
 @pytest.mark.parametrize("ds,x0,y0,w,h,D", OP_CASES)
-def test_operator_parity(ctx, oracle, ds, x0, y0, w, h, D):
+def test_operator_parity(ctx, oracle, op_family, ds, x0, y0, w, h, D):
     L, R = crop_pair(ds, x0, y0, w, h)
     p = P(ndisp=D)
     T, n = 33, w * h
@@ -117,6 +125,49 @@ def test_operator_parity(ctx, oracle, ds, x0, y0, w, h, D):
     assert_bit_equal(o_r.download((h, w, 4), np.uint8), ow["right"], "WTA right image")
     for buf, key in zip(f, ("d_ref", "d_tar", "conf_ref", "conf_tar")):
         assert_bit_equal(buf.download((h, w), np.float32), ow[key], f"WTA {key}")
+
+
+def test_operator_chain_full_teddy(ctx, oracle):
+    """main.cpp:463-526 operator by operator (asw_Aggr, 4 x support, r x (V, H), asw_WTA) on the whole teddy pair through
+    the TMA-fed kernels behind the per-operator ABI: bit-identical to the fused call, and its cost beside the fused call."""
+    import time
+    L, R = load_pair("teddy")
+    H, W, _ = L.shape
+    p = P(iterations=3)
+    D, T, n = p.ndisp, 33, W * H
+    fused = run_fused(ctx, L, R, p, keep=True)
+    dl, dr = ctx.to_device(L), ctx.to_device(R)
+    bufs = {k: ctx.alloc(4 * n * D) for k in ("a", "b")}
+    tabs = {k: ctx.alloc(4 * n * T) for k in ("vl", "hl", "vr", "hr")}
+    o_l, f_d, f_c = ctx.alloc(4 * n), ctx.alloc(4 * n), ctx.alloc(4 * n)
+
+    def chain():
+        ctx.asw_Aggr(dl.ptr, dr.ptr, W, H, p, bufs["a"].ptr)
+        ctx.asw_vSupport(dl.ptr, W, H, p, tabs["vl"].ptr)
+        ctx.asw_hSupport(dl.ptr, W, H, p, tabs["hl"].ptr)
+        ctx.asw_vSupport(dr.ptr, W, H, p, tabs["vr"].ptr)
+        ctx.asw_hSupport(dr.ptr, W, H, p, tabs["hr"].ptr)
+        for _ in range(p.iterations):
+            ctx.asw_vCostAggregation(W, H, p, tabs["vl"].ptr, tabs["vr"].ptr, bufs["a"].ptr, None, bufs["b"].ptr)
+            ctx.asw_hCostAggregation(W, H, p, tabs["hl"].ptr, tabs["hr"].ptr, bufs["b"].ptr, None, bufs["a"].ptr)
+        ctx.asw_WTA(W, H, p, bufs["a"].ptr, o_l.ptr, f_d.ptr, None, None, f_c.ptr, None)
+        ctx.sync()
+
+    chain()
+    assert_bit_equal(bufs["a"].download((D, H, W), np.float32), fused["cost"], "operator chain: final volume")
+    assert_bit_equal(o_l.download((H, W, 4), np.uint8), fused["left"], "operator chain: disparity image")
+    assert_bit_equal(f_d.download((H, W), np.float32), fused["d"].astype(np.float32), "operator chain: d_est_reference")
+    assert_bit_equal(f_c.download((H, W), np.float32), fused["conf"], "operator chain: confidence")
+    t0 = time.perf_counter()
+    for _ in range(5):
+        chain()
+    t_chain = (time.perf_counter() - t0) / 5
+    t0 = time.perf_counter()
+    for _ in range(5):
+        run = ctx.disparity_raw(dl.ptr, dr.ptr, W, H, p, o_l.ptr, None, f_c.ptr)
+    ctx.sync()
+    t_fused = (time.perf_counter() - t0) / 5
+    print("operator chain %.3f ms, fused call %.3f ms (teddy, r=3)" % (t_chain * 1e3, t_fused * 1e3))
 
 
 # ---------------------------------------------------------------------------------------------
