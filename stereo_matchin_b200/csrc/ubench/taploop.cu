@@ -316,11 +316,18 @@ int main(int argc, char** argv) {
 #define RUN_H(F, MB, CPS) run("h_flags" #F "_minb" #MB "_cps" #CPS, k_h<F, MB>, 128, CPS, (CPS > 3 ? 49152 : 65536), (CPS > 3 ? 12288 : 16384), HS, 33.0 * 64, 33.0, "warptaps")
     constexpr int VST = 8 * 4 * 32 + 8 * 96 * 4 + 4 * 32 * 68;
 #define RUN_V(F, NWP, MB, CPS, NST) run("v_flags" #F "_nw" #NWP "_minb" #MB "_cps" #CPS, k_v<F, NWP, MB>, NWP * 32, CPS, (size_t)NST * VST * 4, NST * VST, VS, 512.0, 1.0, "warpsteps")
-    if (sel == 0) {
-    RUN_H(15, 2, 2);
-    RUN_H(31, 2, 2);
-    RUN_H(15, 3, 3);
-    RUN_H(31, 3, 3);
-    }
+    (void)sel;
+    // 1. cost of a shared-memory load instruction (SM cycles per warp-level load, all registers consumed by FFMAs)
+#define RL(W, P) run_lds<W, P>("lds" #W "B_pat" #P)
+    RL(16, 0); RL(16, 1); RL(16, 2); RL(16, 3); RL(16, 4); RL(16, 5); RL(16, 6); RL(16, 7); RL(16, 9); RL(16, 10); RL(16, 11); RL(16, 14); RL(16, 17); RL(16, 18);
+    RL(8, 0); RL(8, 1); RL(8, 2); RL(8, 5); RL(8, 9); RL(8, 10);
+    RL(4, 0); RL(4, 1);
+    // 2. tap loop of the horizontal pass: pieces switched off, occupancy 1-4 warps per scheduler
+    RUN_H(15, 2, 2); RUN_H(31, 2, 2); RUN_H(13, 2, 2); RUN_H(14, 2, 2); RUN_H(11, 2, 2); RUN_H(9, 2, 2); RUN_H(10, 2, 2); RUN_H(12, 2, 2);
+    RUN_H(15, 2, 1); RUN_H(15, 3, 3); RUN_H(15, 4, 4);
+    // 3. step loop of the vertical pass: pieces switched off, cost prefetch, staggered warps, quad-rule lanes
+    RUN_V(15, 8, 1, 1, 3); RUN_V(31, 8, 1, 1, 3); RUN_V(47, 8, 1, 1, 3); RUN_V(79, 8, 1, 1, 3);
+    RUN_V(13, 8, 1, 1, 3); RUN_V(14, 8, 1, 1, 3); RUN_V(11, 8, 1, 1, 3);
+    RUN_V(15, 12, 1, 1, 3); RUN_V(15, 16, 1, 1, 3);
     return 0;
 }
