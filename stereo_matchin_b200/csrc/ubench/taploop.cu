@@ -198,6 +198,74 @@ __global__ void __launch_bounds__(NWARP * 32, MINB) k_v(float* out, long long* c
     if (threadIdx.x == 0) cyc[blockIdx.x] = (long long)(tmax - tmin);
 }
 
+
+// V loop, input-row-major order: per step the 4 input rows are walked in the outer loop (8 cost values live instead of 32,
+// the loads of row r+1 run under the math of row r), the right weights are read as scalars per (row, tap).
+template <int NWARP>
+__global__ void __launch_bounds__(NWARP * 32, 1) k_v_rowmajor(float* out, long long* cyc, int nsteps, int smem_floats) {
+    extern __shared__ __align__(128) float sm[];
+    for (int i = threadIdx.x; i < smem_floats; i += blockDim.x) sm[i] = 1.0f + (float)(i & 1023) * 1e-4f;
+    __syncthreads();
+    constexpr int XW = 32, WRC = 96, kVCols = 68, kVWL = 8 * 4 * XW, kVWR = 8 * WRC * 4, STAGE = kVWL + kVWR + 4 * XW * kVCols;
+    const int tid = threadIdx.x, w = (tid >> 5) & 7, lane = tid & 31;
+    const int tw = w, el[2] = {lane, lane + 32};
+    f32x2 acc[8][2][2];
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+#pragma unroll
+        for (int jp = 0; jp < 2; jp++)
+#pragma unroll
+            for (int ee = 0; ee < 2; ee++) acc[k][jp][ee] = pack2(1e-5f, 1e-5f);
+    const int nstage = smem_floats / STAGE;
+    const long long t0 = clock64();
+    for (int g = 0; g < nsteps; g++) {
+        const float* sWL = sm + (g % nstage) * STAGE;
+        const float* sWR = sWL + kVWL;
+        const float* sC = sWR + kVWR + (4 * tw) * kVCols;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            f32x2 c2[2][2];
+#pragma unroll
+            for (int jp = 0; jp < 2; jp++)
+#pragma unroll
+                for (int ee = 0; ee < 2; ee++) {
+                    const float* p = sC + (r * XW + 2 * jp) * kVCols + el[ee] + 2 * jp;
+                    c2[jp][ee] = pack2(lds32(p), lds32(p + kVCols + 1));
+                }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const float4 l4 = lds128(sWL + (k * 4 + r) * XW + 4 * tw);
+                const f32x2 wl2[2] = {pack2(l4.x, l4.y), pack2(l4.z, l4.w)};
+#pragma unroll
+                for (int ee = 0; ee < 2; ee++) {
+                    const float wv = lds32(sWR + (k * WRC + 4 * tw + 63 - el[ee]) * 4 + r);
+                    const f32x2 wrr = pack2(wv, wv);
+#pragma unroll
+                    for (int jp = 0; jp < 2; jp++) {
+                        const f32x2 ww = mul2(wl2[jp], wrr);
+                        acc[k][jp][ee] = fma2(ww, c2[jp][ee], acc[k][jp][ee]);
+                    }
+                }
+            }
+        }
+    }
+    const long long t1 = clock64();
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+#pragma unroll
+        for (int jp = 0; jp < 2; jp++)
+#pragma unroll
+            for (int ee = 0; ee < 2; ee++) { float a, b; unpack2(acc[k][jp][ee], a, b); s += a + b; }
+    if (s == 123.456f) out[0] = s;
+    __shared__ unsigned long long tmin, tmax;
+    if (threadIdx.x == 0) { tmin = ~0ull; tmax = 0ull; }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { atomicMin(&tmin, (unsigned long long)t0); atomicMax(&tmax, (unsigned long long)t1); }
+    __syncthreads();
+    if (threadIdx.x == 0) cyc[blockIdx.x] = (long long)(tmax - tmin);
+}
+
 static int g_sms = 0;
 static float* g_out;
 static long long* g_cyc;
@@ -317,6 +385,14 @@ int main(int argc, char** argv) {
     constexpr int VST = 8 * 4 * 32 + 8 * 96 * 4 + 4 * 32 * 68;
 #define RUN_V(F, NWP, MB, CPS, NST) run("v_flags" #F "_nw" #NWP "_minb" #MB "_cps" #CPS, k_v<F, NWP, MB>, NWP * 32, CPS, (size_t)NST * VST * 4, NST * VST, VS, 512.0, 1.0, "warpsteps")
     (void)sel;
+    if (sel == 2) {
+        constexpr int VST2 = 8 * 4 * 32 + 8 * 96 * 4 + 4 * 32 * 68;
+        RUN_V(15, 8, 1, 1, 3);
+        run("v_rowmajor_nw8", k_v_rowmajor<8>, 256, 1, (size_t)3 * VST2 * 4, 3 * VST2, VS, 512.0, 1.0, "warpsteps");
+        run("v_rowmajor_nw12", k_v_rowmajor<12>, 384, 1, (size_t)3 * VST2 * 4, 3 * VST2, VS, 512.0, 1.0, "warpsteps");
+        run("v_rowmajor_nw16", k_v_rowmajor<16>, 512, 1, (size_t)3 * VST2 * 4, 3 * VST2, VS, 512.0, 1.0, "warpsteps");
+        return 0;
+    }
     // 1. cost of a shared-memory load instruction (SM cycles per warp-level load, all registers consumed by FFMAs)
 #define RL(W, P) run_lds<W, P>("lds" #W "B_pat" #P)
     RL(16, 0); RL(16, 1); RL(16, 2); RL(16, 3); RL(16, 4); RL(16, 5); RL(16, 6); RL(16, 7); RL(16, 9); RL(16, 10); RL(16, 11); RL(16, 14); RL(16, 17); RL(16, 18);
