@@ -232,20 +232,117 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_v_rowmajor(float* out, long l
                     const float* p = sC + (r * XW + 2 * jp) * kVCols + el[ee] + 2 * jp;
                     c2[jp][ee] = pack2(lds32(p), lds32(p + kVCols + 1));
                 }
+            float4 l4[8];
+            float wv[8][2];
 #pragma unroll
             for (int k = 0; k < 8; k++) {
-                const float4 l4 = lds128(sWL + (k * 4 + r) * XW + 4 * tw);
-                const f32x2 wl2[2] = {pack2(l4.x, l4.y), pack2(l4.z, l4.w)};
+                l4[k] = lds128(sWL + (k * 4 + r) * XW + 4 * tw);
+#pragma unroll
+                for (int ee = 0; ee < 2; ee++) wv[k][ee] = lds32(sWR + (k * WRC + 4 * tw + 63 - el[ee]) * 4 + r);
+            }
+            // operand-reuse order: the 8 output rows of one (column pair, diagonal) back to back -- their FFMA2s share the cost pair
+#pragma unroll
+            for (int jp = 0; jp < 2; jp++)
 #pragma unroll
                 for (int ee = 0; ee < 2; ee++) {
-                    const float wv = lds32(sWR + (k * WRC + 4 * tw + 63 - el[ee]) * 4 + r);
-                    const f32x2 wrr = pack2(wv, wv);
+                    f32x2 ww[8];
 #pragma unroll
-                    for (int jp = 0; jp < 2; jp++) {
-                        const f32x2 ww = mul2(wl2[jp], wrr);
-                        acc[k][jp][ee] = fma2(ww, c2[jp][ee], acc[k][jp][ee]);
-                    }
+                    for (int k = 0; k < 8; k++)
+                        ww[k] = mul2(jp == 0 ? pack2(l4[k].x, l4[k].y) : pack2(l4[k].z, l4[k].w), pack2(wv[k][ee], wv[k][ee]));
+#pragma unroll
+                    for (int k = 0; k < 8; k++) acc[k][jp][ee] = fma2(ww[k], c2[jp][ee], acc[k][jp][ee]);
                 }
+        }
+    }
+    const long long t1 = clock64();
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+#pragma unroll
+        for (int jp = 0; jp < 2; jp++)
+#pragma unroll
+            for (int ee = 0; ee < 2; ee++) { float a, b; unpack2(acc[k][jp][ee], a, b); s += a + b; }
+    if (s == 123.456f) out[0] = s;
+    __shared__ unsigned long long tmin, tmax;
+    if (threadIdx.x == 0) { tmin = ~0ull; tmax = 0ull; }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { atomicMin(&tmin, (unsigned long long)t0); atomicMax(&tmax, (unsigned long long)t1); }
+    __syncthreads();
+    if (threadIdx.x == 0) cyc[blockIdx.x] = (long long)(tmax - tmin);
+}
+
+
+// V loop, second order: input rows in pairs (r2), right weights as LDS.64 (2 taps of one column), and for every
+// (input row, column pair, diagonal) the 8 output rows back to back: 8 FMUL2 then 8 FFMA2 that share the cost pair
+// (operand-reuse cache: an FFMA2 with three distinct register pairs needs 3 register-file cycles, 2 with one reused).
+//   REMAP: quad-rule lanes (4 adjacent lanes read 2 right-weight columns)   ORDER 0: FMUL2/FFMA2 per k, 1: 8 + 8
+__device__ __forceinline__ void lds64(const void* p, float& a, float& b) {
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(b) : "r"(smem_u32(p)));
+}
+template <int REMAP, int ORDER>
+__global__ void __launch_bounds__(256, 1) k_v_rm2(float* out, long long* cyc, int nsteps, int smem_floats) {
+    extern __shared__ __align__(128) float sm[];
+    for (int i = threadIdx.x; i < smem_floats; i += blockDim.x) sm[i] = 1.0f + (float)(i & 1023) * 1e-4f;
+    __syncthreads();
+    constexpr int XW = 32, WRC = 96, kVCols = 68, kVWL = 8 * 4 * XW, kVWR = 8 * WRC * 4, STAGE = kVWL + kVWR + 4 * XW * kVCols;
+    const int tid = threadIdx.x, w = (tid >> 5) & 7, lane = tid & 31;
+    int tw, el[2];
+    if (REMAP) { tw = (w & 3) + 4 * ((lane >> 1) & 1); el[0] = 2 * (lane >> 2) + (lane & 1) + 16 * ((lane >> 1) & 1) + 16 * (w >> 2); el[1] = (el[0] + 32) & 63; }
+    else { tw = w; el[0] = lane; el[1] = lane + 32; }
+    f32x2 acc[8][2][2];
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+#pragma unroll
+        for (int jp = 0; jp < 2; jp++)
+#pragma unroll
+            for (int ee = 0; ee < 2; ee++) acc[k][jp][ee] = pack2(1e-5f, 1e-5f);
+    const int nstage = smem_floats / STAGE;
+    const long long t0 = clock64();
+    for (int g = 0; g < nsteps; g++) {
+        const float* sWL = sm + (g % nstage) * STAGE;
+        const float* sWR = sWL + kVWL;
+        const float* sC = sWR + kVWR + (4 * tw) * kVCols;
+#pragma unroll
+        for (int r2 = 0; r2 < 2; r2++) {
+            f32x2 c2[2][2][2];
+            float wv[8][2][2];
+#pragma unroll
+            for (int rr = 0; rr < 2; rr++)
+#pragma unroll
+                for (int jp = 0; jp < 2; jp++)
+#pragma unroll
+                    for (int ee = 0; ee < 2; ee++) {
+                        const float* p = sC + ((2 * r2 + rr) * XW + 2 * jp) * kVCols + el[ee] + 2 * jp;
+                        c2[rr][jp][ee] = pack2(lds32(p), lds32(p + kVCols + 1));
+                    }
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+#pragma unroll
+                for (int ee = 0; ee < 2; ee++) lds64(sWR + (k * WRC + 4 * tw + 63 - el[ee]) * 4 + 2 * r2, wv[k][ee][0], wv[k][ee][1]);
+#pragma unroll
+            for (int rr = 0; rr < 2; rr++) {
+                float4 l4[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) l4[k] = lds128(sWL + (k * 4 + 2 * r2 + rr) * XW + 4 * tw);
+#pragma unroll
+                for (int jp = 0; jp < 2; jp++)
+#pragma unroll
+                    for (int ee = 0; ee < 2; ee++) {
+                        if (ORDER == 1) {
+                            f32x2 ww[8];
+#pragma unroll
+                            for (int k = 0; k < 8; k++)
+                                ww[k] = mul2(jp == 0 ? pack2(l4[k].x, l4[k].y) : pack2(l4[k].z, l4[k].w), pack2(wv[k][ee][rr], wv[k][ee][rr]));
+#pragma unroll
+                            for (int k = 0; k < 8; k++) acc[k][jp][ee] = fma2(ww[k], c2[rr][jp][ee], acc[k][jp][ee]);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 8; k++) {
+                                const f32x2 ww = mul2(jp == 0 ? pack2(l4[k].x, l4[k].y) : pack2(l4[k].z, l4[k].w), pack2(wv[k][ee][rr], wv[k][ee][rr]));
+                                acc[k][jp][ee] = fma2(ww, c2[rr][jp][ee], acc[k][jp][ee]);
+                            }
+                        }
+                    }
             }
         }
     }
@@ -269,6 +366,66 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_v_rowmajor(float* out, long l
 static int g_sms = 0;
 static float* g_out;
 static long long* g_cyc;
+
+// Register-file read bandwidth of packed FMAs: a stream of FFMA2 on 32 accumulator pairs whose multiplicand pairs
+//   MODE 0: both change with every instruction (3 distinct 64-bit sources per FFMA2, nothing for the operand-reuse cache)
+//   MODE 1: operand b is the same for 8 consecutive instructions       MODE 2: a and b the same for 8 consecutive
+//   MODE 3: like 0 but b is a scalar register (.F32 form)               MODE 4: scalar FFMA (32-bit), 3 distinct sources
+template <int MODE>
+__global__ void __launch_bounds__(512) k_rf(float* out, long long* cyc, int iters, const float* __restrict__ in) {
+    f32x2 acc[16], a[8], b[8];
+    float bs[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { a[i] = pack2(in[i] + threadIdx.x, in[i + 16]); b[i] = pack2(in[i + 32], in[i + 48] + threadIdx.x); bs[i] = in[i + 64] + threadIdx.x; }
+#pragma unroll
+    for (int i = 0; i < 16; i++) acc[i] = pack2((float)i, 1.0f);
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int rep = 0; rep < 2; rep++)
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            if (MODE == 0) acc[i] = fma2(a[i & 7], b[(i * 5 + 3 + rep) & 7], acc[i]);
+            else if (MODE == 1) acc[i] = fma2(a[i & 7], b[(i >> 3) + 2 * rep], acc[i]);
+            else if (MODE == 2) acc[i] = fma2(a[(i >> 3) + 2 * rep], b[(i >> 3) + 2 * rep], acc[i]);
+            else if (MODE == 3) acc[i] = fma2(a[i & 7], pack2(bs[(i * 5 + 3 + rep) & 7], bs[(i * 5 + 3 + rep) & 7]), acc[i]);
+            else {
+                float lo, hi;
+                unpack2(acc[i], lo, hi);
+                lo = __fmaf_rn(bs[i & 7], bs[(i * 5 + 3 + rep) & 7], lo);
+                hi = __fmaf_rn(bs[(i + 3) & 7], bs[(i * 3 + 1 + rep) & 7], hi);
+                acc[i] = pack2(lo, hi);
+            }
+        }
+    }
+    const long long t1 = clock64();
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; i++) { float x, y; unpack2(acc[i], x, y); s += x + y; }
+    if (s == 123.456f) out[0] = s;
+    __shared__ unsigned long long tmin, tmax;
+    if (threadIdx.x == 0) { tmin = ~0ull; tmax = 0ull; }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { atomicMin(&tmin, (unsigned long long)t0); atomicMax(&tmax, (unsigned long long)t1); }
+    __syncthreads();
+    if (threadIdx.x == 0) cyc[blockIdx.x] = (long long)(tmax - tmin);
+}
+
+template <int MODE>
+static void run_rf(const char* name, int threads, float* in, float* out, long long* cycp, int sms) {
+    const int iters = 4000;
+    for (int rep = 0; rep < 2; rep++) k_rf<MODE><<<sms, threads>>>(out, cycp, iters, in);
+    cudaDeviceSynchronize();
+    static long long h[4096];
+    cudaMemcpy(h, cycp, sizeof(long long) * sms, cudaMemcpyDeviceToHost);
+    double sum = 0;
+    for (int i = 0; i < sms; i++) sum += (double)h[i];
+    const int wps = threads / 128;                               // warps per scheduler
+    const double per = sum / sms / ((double)iters * 32 * wps);   // SMSP cycles per warp-level instruction (mode 4: per pair of scalar FFMAs)
+    printf("{\"name\": \"%s\", \"warps_per_smsp\": %d, \"smsp_cycles_per_instruction\": %.3f}\n", name, wps, per);
+    fflush(stdout);
+}
 
 // ---------------------------------------------------------------------------------------------------
 // LDS cost: 16 unrolled loads per iteration, every loaded register consumed by FFMAs (2 per LDS.128, FMA pipe),
@@ -385,6 +542,26 @@ int main(int argc, char** argv) {
     constexpr int VST = 8 * 4 * 32 + 8 * 96 * 4 + 4 * 32 * 68;
 #define RUN_V(F, NWP, MB, CPS, NST) run("v_flags" #F "_nw" #NWP "_minb" #MB "_cps" #CPS, k_v<F, NWP, MB>, NWP * 32, CPS, (size_t)NST * VST * 4, NST * VST, VS, 512.0, 1.0, "warpsteps")
     (void)sel;
+    if (sel == 3) {
+        float* in;
+        cudaMalloc(&in, 1024);
+        cudaMemset(in, 0, 1024);
+#define RF(M, T) run_rf<M>("rf_mode" #M "_threads" #T, T, in, g_out, g_cyc, g_sms)
+        RF(0, 128); RF(0, 256); RF(0, 512);
+        RF(1, 128); RF(1, 256); RF(1, 512);
+        RF(2, 128); RF(2, 256); RF(2, 512);
+        RF(3, 128); RF(3, 256); RF(3, 512);
+        RF(4, 128); RF(4, 256); RF(4, 512);
+        return 0;
+    }
+    if (sel == 4) {
+        constexpr int VST4 = 8 * 4 * 32 + 8 * 96 * 4 + 4 * 32 * 68;
+        RUN_V(15, 8, 1, 1, 3);
+        RUN_V(31, 8, 1, 1, 3);
+#define RM2(RE, OR) run("v_rm2_remap" #RE "_order" #OR, k_v_rm2<RE, OR>, 256, 1, (size_t)3 * VST4 * 4, 3 * VST4, VS, 512.0, 1.0, "warpsteps")
+        RM2(0, 0); RM2(0, 1); RM2(1, 0); RM2(1, 1);
+        return 0;
+    }
     if (sel == 2) {
         constexpr int VST2 = 8 * 4 * 32 + 8 * 96 * 4 + 4 * 32 * 68;
         RUN_V(15, 8, 1, 1, 3);
