@@ -10,16 +10,17 @@ dl, dr = ctx.to_device(L), ctx.to_device(R)
 od = ctx.alloc(W * H)
 p = api.AswParams(ndisp=D, iterations=3)
 lib = api.load_library()
-out = (C.c_ulonglong * 8)()
+out = (C.c_ulonglong * 16)()
 tm = ctx.disparity_raw(dl.ptr, dr.ptr, W, H, p, None, od.ptr, None, timing=True)
 lib.asw_debug_vprof(out)
 tm = ctx.disparity_raw(dl.ptr, dr.ptr, W, H, p, None, od.ptr, None, timing=True)
 lib.asw_debug_vprof(out)
 v = [int(x) for x in out]
-n = v[4]
+n = v[8]
 print("warp-steps", n, "vagg_ms", tm["vagg_mean_ms"])
-names = ["bookkeeping(before wait)", "full-barrier wait", "cost loads + math + arrive", "epilogue", ]
-tot = sum(v[:4])
-for nm, x in zip(names, v[:4]):
-    print("%-30s %8.1f cycles/warp-step  %5.1f%%" % (nm, x / n, 100.0 * x / tot))
+names = ["before the barrier", "full-barrier wait", "step qs=0 (+finalize rows 4-7)", "step qs=1", "steps qs=2..7", "step qs=8", "step qs=9 (+finalize rows 0-3)", "finalize at tile end"]
+tot = sum(v[:8])
+for nm, x in zip(names, v[:8]):
+    print("%-32s %8.1f cycles per warp-step (all steps)  %5.1f%%" % (nm, x / n, 100.0 * x / tot))
 print("total per warp-step", tot / n)
+print("per occurrence: qs0 %.0f  qs1 %.0f  qs2-7 %.0f  qs8 %.0f  qs9 %.0f cycles" % tuple(v[i] / (n / 10 * k) for i, k in ((2, 1), (3, 1), (4, 6), (5, 1), (6, 1))))

@@ -1084,4 +1084,22 @@ int asw_host_free(asw_ctx* ctx, void* p) {
     return ASW_OK;
 }
 
+#ifdef ASW_VPROF
+// instrumented builds only: the vertical pass' private denominator buffer of the last call (scripts/race_probe.py)
+__attribute__((visibility("default"))) long long asw_debug_vden(asw_ctx* ctx, float* out_host, long long max_floats) {
+    cudaDeviceSynchronize();
+    long long n = (long long)(ctx->den_v.cap / sizeof(float));
+    if (n > max_floats) n = max_floats;
+    if (out_host && n > 0) cudaMemcpy(out_host, ctx->den_v.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost);
+    return n;
+}
+// instrumented builds only (scripts/vprof.py): reads and clears the vertical pass' phase counters
+__attribute__((visibility("default"))) int asw_debug_vprof(unsigned long long* out16) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out16, asw::g_vprof, sizeof(unsigned long long) * 16);
+    static const unsigned long long zero[16] = {0};
+    cudaMemcpyToSymbol(asw::g_vprof, zero, sizeof zero);
+    return 0;
+}
+#endif
 }  // extern "C"
