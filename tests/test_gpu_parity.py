@@ -336,6 +336,33 @@ def test_full_size_cfg3_is_deterministic(ctx):
     assert_bit_equal(a["cost"][:, 1000:1016], c["cost"], "cfg3 final volume vs generic CUDA kernels")
 
 
+def test_full_size_cfg3_repeatable_over_many_runs(ctx):
+    """Stress form of the determinism test: 7 iterations (six vertical passes that read their denominators back, every
+    ring stage released and refilled ~17 000 times per SM), 16 runs, disparity and confidence maps compared bit for bit.
+    Round 2 found a release of a ring stage that ptxas had scheduled in front of the multiply-adds that consume the
+    stage's last loads: one run in eight differed in a few hundred pixels; the two-run test above rarely caught it."""
+    from stereo_matchin_b200.synth import make_config
+    L, R, _, D = make_config("cfg3_1800x1500_d256")
+    H, W, _ = L.shape
+    p = P(ndisp=D, iterations=7)
+    dl, dr = ctx.to_device(L), ctx.to_device(R)
+    od, oc = ctx.alloc(W * H), ctx.alloc(W * H * 4)
+    ref_d = ref_c = None
+    try:
+        for run in range(16):
+            ctx.disparity_raw(dl.ptr, dr.ptr, W, H, p, None, od.ptr, oc.ptr)
+            ctx.sync()
+            d, c = od.download((H, W), np.uint8), oc.download((H, W), np.float32)
+            if ref_d is None:
+                ref_d, ref_c = d, c
+            else:
+                assert_bit_equal(d, ref_d, f"cfg3 disparity map, run {run} vs run 0")
+                assert_bit_equal(c, ref_c, f"cfg3 confidence map, run {run} vs run 0")
+    finally:
+        for b in (dl, dr, od, oc):
+            b.free()
+
+
 def test_full_size_cfg3_properties(ctx, oracle):
     from stereo_matchin_b200.synth import make_config
     L, R, _, D = make_config("cfg3_1800x1500_d256")
