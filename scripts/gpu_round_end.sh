@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 timeout 120 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"
 timeout 900 python -m pytest tests -m gpu -q --timeout=600 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
 timeout 300 python scripts/ubench.py > gpurun_out/ubench.json 2>&1; echo "ubench rc=$?"
-[ -x scripts/taploop.bin ] && timeout 200 scripts/taploop.bin 1 > gpurun_out/taploop.jsonl 2>&1; echo "taploop rc=$?"
+[ -x scripts/taploop.bin ] && { timeout 200 scripts/taploop.bin 1 > gpurun_out/taploop.jsonl 2>&1; timeout 60 scripts/taploop.bin 3 >> gpurun_out/taploop.jsonl 2>&1; timeout 60 scripts/taploop.bin 4 >> gpurun_out/taploop.jsonl 2>&1; }; echo "taploop rc=$?"
 timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_cfg3.json 2> gpurun_out/bench_cfg3.err; echo "bench rc=$?"; cat gpurun_out/bench_cfg3.json
 timeout 300 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_short.json 2>&1 && \
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/bench_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
