@@ -218,10 +218,11 @@ ASW_API int asw_merge_shards(asw_ctx* ctx, int W, int rows, int ndisp, int nshar
  * above, rows of the processed band) for consumers such as the right-view WTA / consistency
  * check.  Returns NULL if the last call did not hand it out.  Enable with
  * asw_set_keep_volume(ctx, 1): the final volume is then converted from the kernels' own
- * layout to the reference layout (one extra pass over the volume).  Default 0.  (The final
- * volume always exists in HBM in the kernels' layout: winner-take-all is a separate kernel
- * that reads it; fusing it into the last horizontal pass was measured and did not pay,
- * DESIGN.md section 5.) */
+ * layout to the reference layout (one extra pass over the volume).  Default 0.  With the
+ * default 0 the last horizontal pass takes the winner inside its epilogue (per 128-disparity
+ * window, merged by a small kernel) and the final volume is never written to HBM; with 1
+ * (and for disparity shards) the volume is written and the separate WTA kernel reads it.
+ * Both give identical bits. */
 ASW_API int asw_set_keep_volume(asw_ctx* ctx, int keep);
 ASW_API const float* asw_final_volume(asw_ctx* ctx);
 

@@ -46,6 +46,7 @@ struct asw_ctx {
     Scratch vL, hL, vR, hR;                // support tables
     Scratch vol[3];                        // cost volumes (raw / ping / pong)
     Scratch den_v, den_h;                  // hoisted denominators
+    Scratch wta_part;                      // per-window (min1, min2, argmin) of the winner-take-all fused into the last H pass
     Scratch vol_ref;                       // final volume in the reference layout (keep_volume)
     Scratch fimg_l, fimg_r;                // images as float4 (r, g, b, 0), sampler conversion applied
     Scratch tail[12];                      // whole-method buffers (asw_stereo)
@@ -272,6 +273,19 @@ int run_band(asw_ctx* ctx, const uint8_t* dl, const uint8_t* dr, int W, int H, i
         const int vA = up ? min(y1, (y0 + R + 7) & ~7) : y0, vB = down ? max(vA, (y1 - R) & ~7) : y1;
         const bool overlap = hx && hx->begin && (up || down) && vB - vA >= 8 && y1 - y0 >= 2 * R;
         const size_t vrow = (size_t)tl.Wv * tl.Dp, hbytes = sizeof(float) * vrow * R;
+        // Winner-take-all inside the epilogue of the last horizontal pass (asw_wta.cl:25-47 on the values still in registers):
+        // the final volume is then never written.  Not when the caller keeps the volume (right view, refinement) or asks for a
+        // disparity shard's partial result.
+        const int nwin = tl.Dp / (tl.Dp % 128 == 0 ? 128 : 64);
+        const bool fuse_wta = r > 0 && hagg_can_fuse_wta() && !ctx->keep_volume && !sh && !(getenv("ASW_FUSE_WTA") && atoi(getenv("ASW_FUSE_WTA")) == 0);
+        const size_t npx = (size_t)W * (y1 - y0);
+        HWtaOut wo{nullptr, nullptr, nullptr, y0, npx};
+        if (fuse_wta) {
+            if ((st = ensure(ctx, ctx->wta_part, sizeof(float) * 3 * (size_t)nwin * npx))) return st;
+            wo.min1 = (float*)ctx->wta_part.p;
+            wo.min2 = wo.min1 + (size_t)nwin * npx;
+            wo.arg = (int*)(wo.min2 + (size_t)nwin * npx);
+        }
         for (int it = 0; it < r; it++) {
             const int ylo = hx ? y0 : max(ya, y0 - (r - 1 - it) * R), yhi = hx ? y1 : min(yb, y1 + (r - 1 - it) * R);
             cudaEvent_t ev_main = nullptr;
@@ -306,7 +320,7 @@ int run_band(asw_ctx* ctx, const uint8_t* dl, const uint8_t* dr, int W, int H, i
                 t.h_end(it);
                 continue;
             }
-            CUL(launch_hagg_v2(s, it == 0, tl, ylo, yhi, hL, hR, vb, den_h, va, &ctx->env));
+            CUL(launch_hagg_v2(s, it == 0, tl, ylo, yhi, hL, hR, vb, den_h, va, &ctx->env, fuse_wta && it + 1 == r ? &wo : nullptr));
             t.h_end(it);
             if (hx && hx->fn && it + 1 < r) {
                 // the next vertical pass reads R rows of each neighbour: hand out our boundary rows (volume rows are contiguous:
@@ -324,7 +338,12 @@ int run_band(asw_ctx* ctx, const uint8_t* dl, const uint8_t* dr, int W, int H, i
             }
         }
         t.e_agg = t.et.mark();
-        CUL(launch_wta_v2(s, tl, y0, y1, y0, Dfull, va, d_rgba, d_d, d_conf, sh ? sh->min1 : nullptr, sh ? sh->min2 : nullptr, sh ? sh->arg : nullptr));
+        if (fuse_wta) {
+            k_wta_merge<<<(unsigned)((npx + 255) / 256), 256, 0, s>>>(wo.min1, wo.min2, wo.arg, nwin, npx, Dfull, (uint32_t*)d_rgba, d_d, d_conf);
+            CUL(cudaGetLastError());
+        } else {
+            CUL(launch_wta_v2(s, tl, y0, y1, y0, Dfull, va, d_rgba, d_d, d_conf, sh ? sh->min1 : nullptr, sh ? sh->min2 : nullptr, sh ? sh->arg : nullptr));
+        }
         t.e_wta = t.et.mark();
         if (ctx->keep_volume) {
             if ((st = ensure(ctx, ctx->vol_ref, sizeof(float) * (size_t)W * (y1 - y0) * D))) return st;
@@ -426,7 +445,7 @@ int asw_destroy(asw_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     Scratch* all[] = {&ctx->img_l, &ctx->img_r, &ctx->out_rgba, &ctx->out_d, &ctx->out_conf, &ctx->vL, &ctx->hL, &ctx->vR,
-                      &ctx->hR, &ctx->vol[0], &ctx->vol[1], &ctx->vol[2], &ctx->den_v, &ctx->den_h, &ctx->vol_ref, &ctx->fimg_l, &ctx->fimg_r};
+                      &ctx->hR, &ctx->vol[0], &ctx->vol[1], &ctx->vol[2], &ctx->den_v, &ctx->den_h, &ctx->wta_part, &ctx->vol_ref, &ctx->fimg_l, &ctx->fimg_r};
     for (Scratch* s : all) if (s->p) cudaFree(s->p);
     for (Scratch& s : ctx->tail) if (s.p) cudaFree(s.p);
     for (Scratch& s : ctx->cb) if (s.p) cudaFree(s.p);
