@@ -336,6 +336,25 @@ def test_full_size_cfg3_is_deterministic(ctx):
     assert_bit_equal(a["cost"][:, 1000:1016], c["cost"], "cfg3 final volume vs generic CUDA kernels")
 
 
+@pytest.mark.parametrize("W,H,D,it", [(450, 375, 61, 3), (333, 77, 200, 2), (70, 40, 256, 1), (129, 33, 130, 2), (40, 17, 1, 2)])
+def test_wta_inside_last_pass_equals_separate_kernel(ctx, W, H, D, it):
+    """The winner-take-all fused into the last horizontal pass (default) and the stand-alone kernel on the stored volume
+    (ASW_FUSE_WTA=0) give the same disparity, image and confidence bits (asw_wta.cl:25-47: strict '<', lowest d wins)."""
+    from stereo_matchin_b200.synth import make_pair
+    L, R, _ = make_pair(W, H, D, seed=7)
+    p = P(ndisp=D, iterations=it)
+    try:
+        os.environ["ASW_FUSE_WTA"] = "1"
+        a = run_fused(ctx, L, R, p)
+        os.environ["ASW_FUSE_WTA"] = "0"
+        b = run_fused(ctx, L, R, p)
+    finally:
+        os.environ.pop("ASW_FUSE_WTA", None)
+    for k in ("d", "left", "conf"):
+        if a[k] is not None:
+            assert_bit_equal(a[k], b[k], f"fused vs separate WTA: {k}")
+
+
 def test_full_size_cfg3_repeatable_over_many_runs(ctx):
     """Stress form of the determinism test: 7 iterations (six vertical passes that read their denominators back, every
     ring stage released and refilled ~17 000 times per SM), 16 runs, disparity and confidence maps compared bit for bit.
