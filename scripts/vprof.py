@@ -24,3 +24,11 @@ for nm, x in zip(names, v[:8]):
     print("%-32s %8.1f cycles per warp-step (all steps)  %5.1f%%" % (nm, x / n, 100.0 * x / tot))
 print("total per warp-step", tot / n)
 print("per occurrence: qs0 %.0f  qs1 %.0f  qs2-7 %.0f  qs8 %.0f  qs9 %.0f cycles" % tuple(v[i] / (n / 10 * k) for i, k in ((2, 1), (3, 1), (4, 6), (5, 1), (6, 1))))
+
+n = v[14]
+if n:
+    print("H pass (k_hagg_split), warp-steps", n, "hagg_ms", tm["hagg_mean_ms"])
+    tot = sum(v[9:14])
+    for nm, x in zip(["between steps (denominator loads issued)", "full-barrier wait", "window fill + 33 taps", "__syncthreads + issue of step m+2", "epilogue (division, stores / WTA)"], v[9:14]):
+        print("%-42s %8.1f cycles per warp-step  %5.1f%%" % (nm, x / n, 100.0 * x / tot))
+    print("total per warp-step", tot / n)
