@@ -517,6 +517,12 @@ def main():
                                    "frac": pass_flops / (min(v_ms, h_ms) * 1e-3) / 1e12 / peak if min(v_ms, h_ms) > 0 else None},
                     "hbm": {"algorithmic_gbs": pass_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0, "peak_gbs": hbm_peak,
                             "bytes_per_pass": pass_bytes}}
+        # the boxes of this pool run this load at their power cap (sw_power_cap): the FMA rate available at the SM clock
+        # sampled DURING the timed region, beside the fraction against the peak at the maximum clock
+        if clocks and clocks.get("sm_mhz"):
+            peak_clk = 148 * 128 * 2 * clocks["sm_mhz"] * 1e6 / 1e12
+            roofline["frac_at_sampled_sm_clock"] = {"sm_mhz": clocks["sm_mhz"], "peak_tflops_at_that_clock": peak_clk, "frac": achieved / peak_clk,
+                                                    "whole_path_frac": whole / peak_clk}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cpu, _ = oracle_sample(pairs[0][0], pairs[0][1], D, r, args.cpu_rows)
