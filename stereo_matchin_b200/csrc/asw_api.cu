@@ -53,6 +53,19 @@ struct asw_ctx {
     Scratch cb[10];                        // cross-based method buffers (asw_cross_stereo)
     enum { kMaxEvents = 96 };
     cudaEvent_t ev[kMaxEvents] = {};
+    // CUDA graphs of the hot path, one per call signature (buffers, shape, parameters): the second call with a signature is
+    // captured, later ones replay the graph (the ~30 launches of a frame become one; it matters for sub-millisecond frames)
+    struct GraphKey {
+        const void *dl, *dr, *rgba, *dd, *conf;
+        int W, H, y0, y1, family, fuse_env;
+        asw_params prm;
+    };
+    enum { kGraphSlots = 4 };
+    GraphKey gkey[kGraphSlots] = {};
+    cudaGraphExec_t gexec[kGraphSlots] = {};
+    int gstate[kGraphSlots] = {};          // 0 empty, 1 signature seen once, 2 graph ready
+    int gnext = 0;
+    bool graphs_off = false;
 };
 
 namespace {
@@ -73,8 +86,17 @@ int fail(asw_ctx* c, int status, const char* what, cudaError_t e = cudaSuccess) 
         if (e__ != cudaSuccess) return fail(ctx, ASW_ERR_CUDA, #call, e__); \
     } while (0)
 
+void drop_graphs(asw_ctx* ctx) {
+    for (int i = 0; i < asw_ctx::kGraphSlots; i++) {
+        if (ctx->gexec[i]) cudaGraphExecDestroy(ctx->gexec[i]);
+        ctx->gexec[i] = nullptr;
+        ctx->gstate[i] = 0;
+    }
+}
+
 int ensure(asw_ctx* ctx, Scratch& s, size_t bytes) {
     if (s.cap >= bytes) return ASW_OK;
+    drop_graphs(ctx);                                          // captured launches point into the scratch buffers
     if (s.p) { cudaFree(s.p); s.p = nullptr; s.cap = 0; }
     cudaError_t e = cudaMalloc(&s.p, bytes);
     if (e != cudaSuccess) { s.p = nullptr; cudaGetLastError(); return fail(ctx, ASW_ERR_NOMEM, "cudaMalloc scratch", e); }
@@ -211,8 +233,8 @@ struct HaloX {            // per-iteration halo exchange with the neighbouring r
     void* user = nullptr;
 };
 
-int run_band(asw_ctx* ctx, const uint8_t* dl, const uint8_t* dr, int W, int H, int y0, int y1, const asw_params* p,
-             uint8_t* d_rgba, uint8_t* d_d, float* d_conf, asw_timing* tm, const Shard* sh = nullptr, const HaloX* hx = nullptr) {
+int run_band_impl(asw_ctx* ctx, const uint8_t* dl, const uint8_t* dr, int W, int H, int y0, int y1, const asw_params* p,
+                  uint8_t* d_rgba, uint8_t* d_d, float* d_conf, asw_timing* tm, const Shard* sh, const HaloX* hx) {
     const int R = p->radius, T = 2 * R + 1, Dfull = p->ndisp, r = p->iterations;
     const int sd0 = sh ? sh->d0 : 0, sd1 = sh ? sh->d1 : Dfull;
     const int D = sd1 - sd0;                                   // disparities aggregated by this call
@@ -392,6 +414,73 @@ int run_band(asw_ctx* ctx, const uint8_t* dl, const uint8_t* dr, int W, int H, i
     return ASW_OK;
 }
 
+// run_band_impl, or the CUDA graph captured from it.  A plain call (TMA family, no timing, no kept volume, no shard, no halo
+// exchange) whose signature -- buffers, shape, band, parameters -- repeats is captured on its second occurrence and replayed
+// from then on: one graph launch instead of ~30 kernel launches (frames of the reference's size take ~1 ms).
+// Any reallocation of a scratch buffer drops the graphs (ensure()); ASW_GRAPH=0 switches the mechanism off.
+int run_band(asw_ctx* ctx, const uint8_t* dl, const uint8_t* dr, int W, int H, int y0, int y1, const asw_params* p,
+             uint8_t* d_rgba, uint8_t* d_d, float* d_conf, asw_timing* tm, const Shard* sh = nullptr, const HaloX* hx = nullptr) {
+    static const bool env_off = getenv("ASW_GRAPH") && atoi(getenv("ASW_GRAPH")) == 0;
+    const bool eligible = !env_off && !ctx->graphs_off && !tm && !sh && !hx && !ctx->keep_volume && ctx->family == 0 &&
+                          tma_supported(p->radius, p->ndisp) && p->iterations > 0;
+    if (!eligible) return run_band_impl(ctx, dl, dr, W, H, y0, y1, p, d_rgba, d_d, d_conf, tm, sh, hx);
+    asw_ctx::GraphKey k;
+    memset(&k, 0, sizeof k);
+    k.dl = dl; k.dr = dr; k.rgba = d_rgba; k.dd = d_d; k.conf = d_conf;
+    k.W = W; k.H = H; k.y0 = y0; k.y1 = y1; k.family = ctx->family;
+    k.fuse_env = getenv("ASW_FUSE_WTA") ? atoi(getenv("ASW_FUSE_WTA")) : -1;
+    k.prm = *p;
+    int slot = -1;
+    for (int i = 0; i < asw_ctx::kGraphSlots; i++)
+        if (ctx->gstate[i] && !memcmp(&ctx->gkey[i], &k, sizeof k)) slot = i;
+    if (slot >= 0 && ctx->gstate[slot] == 2) {
+        cudaError_t e = cudaGraphLaunch(ctx->gexec[slot], ctx->stream);
+        if (e != cudaSuccess) return fail(ctx, ASW_ERR_CUDA, "cudaGraphLaunch", e);
+        ctx->final_volume = nullptr;
+        return ASW_OK;
+    }
+    if (slot < 0) {                                            // first occurrence: remember the signature, run normally
+        slot = ctx->gnext;
+        ctx->gnext = (ctx->gnext + 1) % asw_ctx::kGraphSlots;
+        if (ctx->gexec[slot]) { cudaGraphExecDestroy(ctx->gexec[slot]); ctx->gexec[slot] = nullptr; }
+        memcpy(&ctx->gkey[slot], &k, sizeof k);
+        ctx->gstate[slot] = 1;
+        return run_band_impl(ctx, dl, dr, W, H, y0, y1, p, d_rgba, d_d, d_conf, tm, sh, hx);
+    }
+    // second occurrence: every scratch buffer already has its size, so the launch sequence can be captured
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        ctx->graphs_off = true;
+        return run_band_impl(ctx, dl, dr, W, H, y0, y1, p, d_rgba, d_d, d_conf, tm, sh, hx);
+    }
+    const int st = run_band_impl(ctx, dl, dr, W, H, y0, y1, p, d_rgba, d_d, d_conf, tm, sh, hx);
+    const cudaError_t ec = cudaStreamEndCapture(ctx->stream, &graph);
+    // the slot may have been cleared by ensure() during the capture (a buffer grew after all): then nothing was cached
+    if (st != ASW_OK || ec != cudaSuccess || !graph || ctx->gstate[slot] != 1 || memcmp(&ctx->gkey[slot], &k, sizeof k)) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        ctx->graphs_off = true;                                // be conservative: this context keeps launching kernel by kernel
+        ctx->gstate[slot] = 0;
+        return run_band_impl(ctx, dl, dr, W, H, y0, y1, p, d_rgba, d_d, d_conf, tm, sh, hx);
+    }
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ei != cudaSuccess || !exec) {
+        cudaGetLastError();
+        ctx->graphs_off = true;
+        ctx->gstate[slot] = 0;
+        return run_band_impl(ctx, dl, dr, W, H, y0, y1, p, d_rgba, d_d, d_conf, tm, sh, hx);
+    }
+    ctx->gexec[slot] = exec;
+    ctx->gstate[slot] = 2;
+    const cudaError_t el = cudaGraphLaunch(exec, ctx->stream);
+    if (el != cudaSuccess) return fail(ctx, ASW_ERR_CUDA, "cudaGraphLaunch", el);
+    ctx->final_volume = nullptr;
+    return ASW_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -444,6 +533,7 @@ int asw_destroy(asw_ctx* ctx) {
     if (!ctx) return ASW_ERR_INVALID;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    drop_graphs(ctx);
     Scratch* all[] = {&ctx->img_l, &ctx->img_r, &ctx->out_rgba, &ctx->out_d, &ctx->out_conf, &ctx->vL, &ctx->hL, &ctx->vR,
                       &ctx->hR, &ctx->vol[0], &ctx->vol[1], &ctx->vol[2], &ctx->den_v, &ctx->den_h, &ctx->wta_part, &ctx->vol_ref, &ctx->fimg_l, &ctx->fimg_r};
     for (Scratch* s : all) if (s->p) cudaFree(s->p);

@@ -355,6 +355,49 @@ def test_wta_inside_last_pass_equals_separate_kernel(ctx, W, H, D, it):
             assert_bit_equal(a[k], b[k], f"fused vs separate WTA: {k}")
 
 
+def test_repeated_calls_replay_a_cuda_graph_with_identical_results(ctx, oracle):
+    """A call signature (buffers, shape, parameters) that repeats is captured into a CUDA graph on its second occurrence and
+    replayed afterwards (asw_api.cu: run_band).  Replays, calls with other signatures in between and a scratch reallocation
+    (a larger frame) must not change a bit; the first result is checked against the oracle."""
+    from stereo_matchin_b200.synth import make_pair
+    La, Ra, _ = make_pair(200, 90, 61, seed=3)
+    Lb, Rb, _ = make_pair(150, 70, 130, seed=4)
+    Lc, Rc, _ = make_pair(640, 300, 200, seed=5)                 # larger: every scratch buffer is reallocated
+    pa, pb, pc = P(ndisp=61, iterations=3), P(ndisp=130, iterations=2), P(ndisp=200, iterations=1)
+
+    def bufs(L, R):
+        H, W, _ = L.shape
+        return ctx.to_device(L), ctx.to_device(R), ctx.alloc(W * H), ctx.alloc(W * H * 4), (H, W)
+
+    def call(b, p):
+        dl, dr, od, oc, (H, W) = b
+        ctx.disparity_raw(dl.ptr, dr.ptr, W, H, p, None, od.ptr, oc.ptr)
+        ctx.sync()
+        return od.download((H, W), np.uint8), oc.download((H, W), np.float32)
+
+    A, B, Cc = bufs(La, Ra), bufs(Lb, Rb), bufs(Lc, Rc)
+    try:
+        ref_a, ref_b = call(A, pa), call(B, pb)
+        o = oracle.asw_hot_path(La, Ra, OP(pa), use_fma=True)
+        assert_bit_equal(ref_a[0].astype(np.float32), o["d_ref"], "first call vs oracle: disparity")
+        assert_bit_equal(ref_a[1], o["conf_ref"], "first call vs oracle: confidence")
+        for rep in range(4):                                     # A: capture, then replays; B interleaved (its own graph)
+            for name, b, p, ref in (("A", A, pa, ref_a), ("B", B, pb, ref_b)):
+                d, c = call(b, p)
+                assert_bit_equal(d, ref[0], f"{name} repetition {rep}: disparity")
+                assert_bit_equal(c, ref[1], f"{name} repetition {rep}: confidence")
+        ref_c = call(Cc, pc)                                     # reallocates the scratch buffers: the graphs must be dropped
+        for rep in range(3):
+            for name, b, p, ref in (("A", A, pa, ref_a), ("C", Cc, pc, ref_c), ("B", B, pb, ref_b)):
+                d, c = call(b, p)
+                assert_bit_equal(d, ref[0], f"{name} after reallocation, repetition {rep}: disparity")
+                assert_bit_equal(c, ref[1], f"{name} after reallocation, repetition {rep}: confidence")
+    finally:
+        for b in (A, B, Cc):
+            for x in b[:4]:
+                x.free()
+
+
 def test_full_size_cfg3_repeatable_over_many_runs(ctx):
     """Stress form of the determinism test: 7 iterations (six vertical passes that read their denominators back, every
     ring stage released and refilled ~17 000 times per SM), 16 runs, disparity and confidence maps compared bit for bit.
