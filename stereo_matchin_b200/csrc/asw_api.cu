@@ -281,10 +281,7 @@ int run_band_impl(asw_ctx* ctx, const uint8_t* dl, const uint8_t* dr, int W, int
         CUL(launch_raw_v2(s, fl, fr, tl, ya, yb, p->trunc, va));
         t.e_raw = t.et.mark();
         const int ws0 = hx ? y0 : ya, ws1 = hx ? y1 : yb;     // rows that are ever aggregated: only they need weights
-        CUL(launch_support_v2(s, true, false, fl, tl, ws0, ws1, p->gamma_c, p->gamma_p, vL));
-        CUL(launch_support_v2(s, false, false, fl, tl, ws0, ws1, p->gamma_c, p->gamma_p, hL));
-        CUL(launch_support_v2(s, true, true, fr, tl, ws0, ws1, p->gamma_c, p->gamma_p, vR));
-        CUL(launch_support_v2(s, false, true, fr, tl, ws0, ws1, p->gamma_c, p->gamma_p, hR));
+        CUL(launch_support4_v2(s, fl, fr, tl, ws0, ws1, p->gamma_c, p->gamma_p, vL, hL, vR, hR));   // main.cpp:470-484, one launch
         t.prev = t.e_supp = t.et.mark();
         // Halo exchange hidden under the interior rows (hx->begin / hx->end): an iteration computes the boundary rows of
         // its horizontal pass first (side stream, concurrently with the interior rows on the main stream), hands them to the
