@@ -132,7 +132,12 @@ ASW_API int asw_disparity_async(asw_ctx* ctx, const uint8_t* left_rgba, const ui
                                 const asw_params* prm, uint8_t* disp_rgba, uint8_t* disp_d, float* conf);
 
 /* Same with DEVICE pointers for inputs and outputs; asynchronous on the context's stream
- * unless `timing` is non-NULL (timing needs the events to complete). */
+ * unless `timing` is non-NULL (timing needs the events to complete).
+ * Launch structure: when a call repeats an earlier one's signature (same buffers, shape, band and parameters; the
+ * CONTENTS of the buffers may differ -- the next frame in the same buffers), its ~26 kernel launches are captured into a
+ * CUDA graph on the second occurrence and replayed from the third on (up to 4 signatures per context; any growth of the
+ * context's scratch memory drops them; calls with `timing`, a kept volume, a shard or a halo exchange are never
+ * captured).  The reference re-enqueues its kernels one by one for every frame (main.cpp:463-526). */
 ASW_API int asw_disparity_device(asw_ctx* ctx, const uint8_t* d_left_rgba, const uint8_t* d_right_rgba, int W, int H,
                                  const asw_params* prm, uint8_t* d_disp_rgba, uint8_t* d_disp_d, float* d_conf,
                                  asw_timing* timing);
